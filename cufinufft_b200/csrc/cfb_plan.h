@@ -1,0 +1,117 @@
+// cfb_plan.h -- internal plan object and stage interfaces of the B200-native
+// cuFINUFFT hot path.  Host C++ behind the C ABI of include/cufinufft.h.
+//
+// Reference counterparts: plan struct include/cufinufft_eitherprec.h:247-297,
+// lifecycle src/cufinufft.cu, allocators src/memtransfer_wrapper.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/cufinufft_opts.h"
+
+namespace cfb {
+
+constexpr int MAX_NS = 16;      // reference MAX_NSPREAD, contrib/spreadinterp.h:10
+constexpr int MAX_NQUAD = 100;  // reference contrib/common.h:10
+
+template <typename T> struct cplx_of;
+template <> struct cplx_of<float>  { using type = float2; };
+template <> struct cplx_of<double> { using type = double2; };
+
+// One owned device allocation that only ever grows (setpts may be called repeatedly
+// on a plan; the reference frees and re-mallocs every time, memtransfer_wrapper.cu:238-279).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename U> U *as() const { return static_cast<U *>(p); }
+};
+
+template <typename T>
+struct Plan {
+    using C = typename cplx_of<T>::type;
+
+    cufinufft_opts opts;
+    int type = 0, dim = 0;
+    int ms = 1, mt = 1, mu = 1;          // modes
+    int nf1 = 1, nf2 = 1, nf3 = 1;       // fine grid
+    int ntransf = 1, maxbatch = 1, iflag = 1;
+    // kernel
+    int ns = 0;
+    T es_beta = 0, es_c = 0, es_halfwidth = 0;
+    // bins
+    int bs[3] = {1, 1, 1};
+    int nbin[3] = {1, 1, 1};
+    int nbins = 1;
+    int method = 0;                      // effective engine: 1 = GM/GM-sort, 2 = SM tiles
+    bool sorted = true;
+    // points (borrowed) + derived (owned)
+    int M = -1;
+    const T *kx = nullptr, *ky = nullptr, *kz = nullptr;
+    DevBuf xs, ys, zs;                   // bin-ordered rescaled coordinates (grid units), T[M]
+    DevBuf sortidx, idxnupts;            // int[M]
+    DevBuf binsize, binstartpts, numsubprob, subprobstartpts, subprob_to_bin;
+    DevBuf scalars;                      // int[8]: [0] totalnumsubprob, [1] work counter, ...
+    DevBuf fw;                           // C[maxbatch * nf1*nf2*nf3]
+    DevBuf fwker[3];                     // T[nf/2+1]
+    DevBuf hostside;                     // device staging for the *_host convenience calls
+    DevBuf hcoef;                        // Horner coefficients [ncoef][ns] as T (kerevalmeth=1)
+    int horner_ncoef = 0;
+    cufftHandle fftplan = 0;
+    bool have_fft = false;
+    cudaStream_t stream = 0;
+    int device = 0;
+    int num_sms = 148;
+    int max_smem_optin = 227 * 1024;
+    // SM-tile geometry (set at makeplan)
+    int tile_pad = 0;                    // ceil(ns/2)
+    int tile_sy = 0, tile_sz = 0;        // padded strides (cells)
+    int tile_cells = 0;
+    int sm_warps = 0;                    // warps per block for the SM spread kernel (0 = SM unusable)
+    // timing / accounting
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int launches_setpts = 0, launches_exec = 0;
+
+    size_t grid_cells() const { return (size_t)nf1 * nf2 * nf3; }
+    size_t nmodes() const { return (size_t)ms * mt * mu; }
+};
+
+// ---- host math (hostmath.cpp) --------------------------------------------
+template <typename T>
+int setup_spreader(T eps, double upsampfac, int kerevalmeth, int *ns, T *beta, T *halfwidth, T *c);
+int next235beven(int n, int b);
+int set_nf_type12(int m, double upsampfac, int ns, int gpu_method, int obinsize);
+void gauss_legendre(int n, double *x, double *w);
+template <typename T>
+void fseries_precomp(int nf, int ns, T beta, T es_c, T halfwidth, T *f, double *a_reim);
+
+// ---- device stages ----------------------------------------------------------
+template <typename T> int stage_fseries(Plan<T> &p);                       // deconv.cu
+template <typename T> int stage_setpts(Plan<T> &p);                        // setpts.cu
+template <typename T> int stage_spread(Plan<T> &p, const typename Plan<T>::C *c, typename Plan<T>::C *fw, int nt);
+template <typename T> int stage_interp(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *fw, int nt);
+template <typename T> int stage_deconvolve(Plan<T> &p, typename Plan<T>::C *fk, const typename Plan<T>::C *fw, int nt);
+template <typename T> int stage_amplify(Plan<T> &p, const typename Plan<T>::C *fk, typename Plan<T>::C *fw, int nt);
+template <typename T> void plan_tile_geometry(Plan<T> &p);                 // spread.cu
+
+#define CFB_CUDA_OK(call)                                                              \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            fprintf(stderr, "[cufinufft-b200] CUDA error %s at %s:%d: %s\n", #call,    \
+                    __FILE__, __LINE__, cudaGetErrorString(e__));                      \
+            return 11;                                                                 \
+        }                                                                              \
+    } while (0)
+
+}  // namespace cfb

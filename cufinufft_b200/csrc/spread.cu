@@ -1,0 +1,106 @@
+// spread.cu -- dimension dispatch for the spread / interp stages and the plan-time
+// choice of the shared-memory tile geometry for the SM spread engine.
+#include <algorithm>
+#include "spreadinterp.cuh"
+
+namespace cfb {
+
+template <typename T>
+int stage_spread(Plan<T> &p, const typename Plan<T>::C *c, typename Plan<T>::C *fw, int nt)
+{
+    if (p.M <= 0 || nt <= 0) return 0;
+    switch (p.dim) {
+        case 1: return launch_spread<T, 1>(p, c, fw, nt);
+        case 2: return launch_spread<T, 2>(p, c, fw, nt);
+        default: return launch_spread<T, 3>(p, c, fw, nt);
+    }
+}
+
+template <typename T>
+int stage_interp(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *fw, int nt)
+{
+    if (p.M <= 0 || nt <= 0) return 0;
+    switch (p.dim) {
+        case 1: return launch_interp<T, 1>(p, c, fw, nt);
+        case 2: return launch_interp<T, 2>(p, c, fw, nt);
+        default: return launch_interp<T, 3>(p, c, fw, nt);
+    }
+}
+
+// Shared-memory wavefronts one point costs for a candidate (sy, rows-per-plane) tile
+// layout: lanes (r, ix) of each pass hit cell r_off + ix; an access of 8-byte cells is
+// served per half-warp over 16 8-byte bank pairs, 16-byte cells per quarter-warp over 8.
+static int layout_cost(int dim, int ns, int sy, int sz, int cell_bytes)
+{
+    const int R = 32 / ns, rows = dim == 1 ? 1 : (dim == 2 ? ns : ns * ns), iters = (rows + R - 1) / R;
+    const int group = cell_bytes == 8 ? 16 : 8, nbank = group;
+    int cost = 0;
+    for (int it = 0; it < iters; ++it) {
+        for (int g0 = 0; g0 < 32; g0 += group) {
+            int mult[16] = {0}, worst = 0;
+            for (int lane = g0; lane < g0 + group; ++lane) {
+                int r = lane / ns, ix = lane - r * ns, row = it * R + r;
+                if (lane >= R * ns || row >= rows) continue;
+                int iz = dim == 3 ? row / ns : 0, iy = dim == 3 ? row - iz * ns : row;
+                int cell = iz * sz + iy * sy + ix;
+                worst = std::max(worst, ++mult[cell % nbank]);
+            }
+            cost += worst;
+        }
+    }
+    return cost;
+}
+
+// Tile = bin + ceil(ns/2) halo on every side (reference: src/2d/spreadinterp2d.cu:171,
+// shared size check src/2d/spread2d_wrapper.cu:647-654), strides padded so that the
+// lane-per-cell passes are bank-conflict free.  Also fixes how many private tiles
+// (= warps) one block carries; 0 means the tile does not fit and the GM engine is used.
+template <typename T>
+void plan_tile_geometry(Plan<T> &p)
+{
+    const int cell = (int)sizeof(typename Plan<T>::C);
+    p.tile_pad = (p.ns + 1) / 2;
+    const int ex = p.bs[0] + 2 * p.tile_pad;
+    const int ey = p.dim > 1 ? p.bs[1] + 2 * p.tile_pad : 1;
+    const int ez = p.dim > 2 ? p.bs[2] + 2 * p.tile_pad : 1;
+    long long best_score = -1;
+    int best_sy = ex, best_rows = ey;
+    const long long base_cells = (long long)ex * ey * ez;
+    for (int sy = ex; sy < ex + 16; ++sy) {
+        for (int rows = ey; rows < ey + (p.dim > 2 ? 16 : 1); ++rows) {
+            long long cells = p.dim == 1 ? sy : (long long)sy * rows * ez;
+            if (cells * 10 > base_cells * 13 && !(sy == ex && rows == ey)) continue;   // <= 30 % padding
+            int cost = layout_cost(p.dim, p.ns, sy, sy * rows, cell);
+            long long score = (long long)cost * 1000000 + cells;
+            if (best_score < 0 || score < best_score) { best_score = score; best_sy = sy; best_rows = rows; }
+        }
+        if (p.dim == 1) break;
+    }
+    if (p.dim == 1) { best_sy = ex; best_rows = 1; }
+    p.tile_sy = p.dim == 1 ? ((ex + 1) & ~1) : best_sy;
+    p.tile_sz = p.tile_sy * best_rows;
+    long long cells = p.dim == 1 ? p.tile_sy : (p.dim == 2 ? (long long)p.tile_sy * ey : (long long)p.tile_sz * ez);
+    cells = (cells + 1) & ~1LL;
+    p.tile_cells = (int)cells;
+    size_t per_warp;
+    switch (p.dim) {
+        case 1: per_warp = sm_spread_smem_per_warp<T, 1>(p.ns, p.tile_cells); break;
+        case 2: per_warp = sm_spread_smem_per_warp<T, 2>(p.ns, p.tile_cells); break;
+        default: per_warp = sm_spread_smem_per_warp<T, 3>(p.ns, p.tile_cells); break;
+    }
+    size_t avail = (size_t)p.max_smem_optin - 18 * 16 * sizeof(T) - 1024;
+    long long w = cells > (1 << 24) ? 0 : (long long)(avail / per_warp);
+    if (w > 16) {                       // several blocks per SM instead of one huge block
+        w = 8;
+    }
+    p.sm_warps = (int)w;
+}
+
+template int stage_spread<float>(Plan<float> &, const float2 *, float2 *, int);
+template int stage_spread<double>(Plan<double> &, const double2 *, double2 *, int);
+template int stage_interp<float>(Plan<float> &, float2 *, const float2 *, int);
+template int stage_interp<double>(Plan<double> &, double2 *, const double2 *, int);
+template void plan_tile_geometry<float>(Plan<float> &);
+template void plan_tile_geometry<double>(Plan<double> &);
+
+}  // namespace cfb

@@ -1,0 +1,137 @@
+// spreadinterp_launch.cuh -- host launch code for the spread / interp kernels; included
+// by the six si_<prec>_d<dim>.cu translation units (one per precision x dimension so the
+// ~140 kernel instantiations compile in parallel).
+//
+// Replaces the reference's method dispatch wrappers CUSPREADnD / CUINTERPnD and their
+// per-transform launch loops (src/2d/spread2d_wrapper.cu:99-164,335-384,615-694,
+// src/2d/interp2d_wrapper.cu:88-274 and the 1-D / 3-D twins): here ONE launch covers
+// all transforms of the batch.
+#pragma once
+#include "spreadinterp.cuh"
+
+namespace cfb {
+
+template <typename T>
+static SIArgs<T> make_args(Plan<T> &p, int nt)
+{
+    SIArgs<T> a;
+    a.xs = p.xs.template as<T>(); a.ys = p.ys.template as<T>(); a.zs = p.zs.template as<T>();
+    a.idx = p.idxnupts.template as<int>();
+    a.c = nullptr; a.fw = nullptr;
+    a.binstart = p.binstartpts.template as<int>(); a.binsize = p.binsize.template as<int>();
+    a.s2b = p.subprob_to_bin.template as<int>(); a.substart = p.subprobstartpts.template as<int>();
+    a.scalars = p.scalars.template as<int>(); a.counter = p.scalars.template as<int>() + 1;
+    a.hcoef = p.hcoef.template as<T>();
+    a.M = p.M; a.nt = nt; a.maxsub = p.opts.gpu_maxsubprobsize;
+    a.nf1 = p.nf1; a.nf2 = p.nf2; a.nf3 = p.nf3;
+    a.bs1 = p.bs[0]; a.bs2 = p.bs[1]; a.bs3 = p.bs[2]; a.nb1 = p.nbin[0]; a.nb2 = p.nbin[1];
+    a.pad = p.tile_pad;
+    a.ex = p.bs[0] + 2 * p.tile_pad; a.ey = p.dim > 1 ? p.bs[1] + 2 * p.tile_pad : 1;
+    a.ez = p.dim > 2 ? p.bs[2] + 2 * p.tile_pad : 1;
+    a.sy = p.tile_sy; a.sz = p.tile_sz; a.tile_cells = p.tile_cells;
+    a.horner = p.opts.gpu_kerevalmeth == 1; a.ncoef = p.horner_ncoef;
+    a.es_c = p.es_c; a.es_beta = p.es_beta;
+    a.fwstride = (long long)p.grid_cells();
+    return a;
+}
+
+template <typename T, int DIM, int NS>
+static int do_spread(Plan<T> &p, SIArgs<T> &a)
+{
+    using C = typename Plan<T>::C;
+    const size_t head = 18 * 16 * sizeof(T);
+    if (p.method == 2 && p.sm_warps > 0) {
+        size_t per_warp = (size_t)p.tile_cells * sizeof(C) + warp_scratch_bytes<T, DIM, NS>();
+        size_t smem = head + (size_t)p.sm_warps * per_warp;
+        CFB_CUDA_OK(cudaFuncSetAttribute(spread_sm_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int blocks_per_sm = (int)((size_t)p.max_smem_optin / (smem + 1024));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        if (blocks_per_sm * p.sm_warps > 32) blocks_per_sm = 32 / p.sm_warps > 0 ? 32 / p.sm_warps : 1;
+        CFB_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(int), p.stream));
+        spread_sm_kernel<T, DIM, NS><<<p.num_sms * blocks_per_sm, 32 * p.sm_warps, smem, p.stream>>>(a);
+    } else {
+        const int warps = 8;
+        size_t smem = head + warps * (warp_scratch_bytes<T, DIM, NS>() + 2 * 32 * sizeof(int));
+        CFB_CUDA_OK(cudaFuncSetAttribute(spread_gm_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long long nb = (((long long)p.M + 31) / 32 * a.nt + warps - 1) / warps;
+        long long cap = (long long)p.num_sms * 8;
+        int blocks = (int)(nb < 1 ? 1 : (nb > cap ? cap : nb));
+        spread_gm_kernel<T, DIM, NS><<<blocks, 32 * warps, smem, p.stream>>>(a);
+    }
+    p.launches_exec++;
+    CFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, int DIM, int NS>
+static int do_interp(Plan<T> &p, SIArgs<T> &a)
+{
+    const size_t head = 18 * 16 * sizeof(T);
+    const int warps = 8;
+    size_t smem = head + warps * (warp_scratch_bytes<T, DIM, NS>() + 2 * 32 * sizeof(int));
+    CFB_CUDA_OK(cudaFuncSetAttribute(interp_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long nb = (((long long)p.M + 31) / 32 * a.nt + warps - 1) / warps;
+    long long cap = (long long)p.num_sms * 8;
+    int blocks = (int)(nb < 1 ? 1 : (nb > cap ? cap : nb));
+    interp_kernel<T, DIM, NS><<<blocks, 32 * warps, smem, p.stream>>>(a);
+    p.launches_exec++;
+    CFB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T> struct max_ns;
+template <> struct max_ns<float>  { static constexpr int v = 9; };   // tol clamps at 6e-8 -> ns <= 9
+template <> struct max_ns<double> { static constexpr int v = 16; };
+
+template <typename T, int DIM, int NS>
+struct NsDispatch {
+    static int spread(Plan<T> &p, SIArgs<T> &a) {
+        if (p.ns == NS) return do_spread<T, DIM, NS>(p, a);
+        return NsDispatch<T, DIM, NS - 1>::spread(p, a);
+    }
+    static int interp(Plan<T> &p, SIArgs<T> &a) {
+        if (p.ns == NS) return do_interp<T, DIM, NS>(p, a);
+        return NsDispatch<T, DIM, NS - 1>::interp(p, a);
+    }
+    static size_t scratch(int ns) {
+        if (ns == NS) return warp_scratch_bytes<T, DIM, NS>();
+        return NsDispatch<T, DIM, NS - 1>::scratch(ns);
+    }
+};
+template <typename T, int DIM>
+struct NsDispatch<T, DIM, 1> {
+    static int spread(Plan<T> &, SIArgs<T> &) { return 10; }
+    static int interp(Plan<T> &, SIArgs<T> &) { return 10; }
+    static size_t scratch(int) { return 0; }
+};
+
+template <typename T, int DIM>
+int launch_spread(Plan<T> &p, const typename Plan<T>::C *c, typename Plan<T>::C *fw, int nt)
+{
+    SIArgs<T> a = make_args(p, nt);
+    a.c = const_cast<typename Plan<T>::C *>(c);
+    a.fw = fw;
+    return NsDispatch<T, DIM, max_ns<T>::v>::spread(p, a);
+}
+
+template <typename T, int DIM>
+int launch_interp(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *fw, int nt)
+{
+    SIArgs<T> a = make_args(p, nt);
+    a.c = c;
+    a.fw = const_cast<typename Plan<T>::C *>(fw);
+    return NsDispatch<T, DIM, max_ns<T>::v>::interp(p, a);
+}
+
+template <typename T, int DIM>
+size_t sm_spread_smem_per_warp(int ns, int tile_cells)
+{
+    return (size_t)tile_cells * sizeof(typename Plan<T>::C) + NsDispatch<T, DIM, max_ns<T>::v>::scratch(ns);
+}
+
+#define CFB_INSTANTIATE_SI(T, DIM)                                                                           \
+    template int launch_spread<T, DIM>(Plan<T> &, const typename Plan<T>::C *, typename Plan<T>::C *, int);  \
+    template int launch_interp<T, DIM>(Plan<T> &, typename Plan<T>::C *, const typename Plan<T>::C *, int);  \
+    template size_t sm_spread_smem_per_warp<T, DIM>(int, int);
+
+}  // namespace cfb

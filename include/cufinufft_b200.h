@@ -1,0 +1,90 @@
+/* include/cufinufft_b200.h -- extension symbols of libcufinufft.so (B200 build).
+ *
+ * The reference's opts struct cannot grow (see cufinufft_opts.h), so everything
+ * the reference does not have goes through these extra extern "C" symbols.
+ * None of them is needed for drop-in use.
+ *
+ *  - stream control + host-pointer convenience calls;
+ *  - stage-level entry points (spread / interp only) replacing the reference's
+ *    internal, C++-mangled CUFINUFFT_SPREADnD / CUFINUFFT_INTERPnD test hooks
+ *    (src/cuspreadinterp.h:278-291, src/2d/spread2d_wrapper.cu:15-97);
+ *  - plan introspection replacing direct reads of the reference's public plan
+ *    struct (include/cufinufft_eitherprec.h:247-297) by tests: bin counts,
+ *    offsets, subproblem map, phihat;
+ *  - per-stage device timings (the reference's -DTIME printf instrumentation,
+ *    src/2d/cufinufft2d.cu:49-89).
+ * Every function returns 0 on success.  "f" suffix = single precision.       */
+#ifndef CUFINUFFT_B200_H
+#define CUFINUFFT_B200_H
+
+#include "cufinufft.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes: 1..9 as the reference (contrib/utils.h:28-36), 10+ are ours */
+enum {
+    CFB_OK = 0,
+    CFB_WARN_EPS_TOO_SMALL = 1,
+    CFB_ERR_UPSAMPFAC_TOO_SMALL = 7,
+    CFB_ERR_HORNER_WRONG_BETA = 8,
+    CFB_ERR_BAD_ARG = 10,       /* NULL plan / bad type, dim, method, bin size ... */
+    CFB_ERR_CUDA = 11,          /* a CUDA runtime call failed (cudaGetLastError text on stderr) */
+    CFB_ERR_CUFFT = 12,
+    CFB_ERR_NOT_IMPLEMENTED = 13, /* type 3 (absent in the reference too, src/cufinufft.cu:533-536) */
+    CFB_ERR_NO_POINTS_SET = 14
+};
+
+const char *cufinufft_b200_version(void);
+
+/* Stream on which all work of the plan is enqueued (default: the legacy default stream 0).
+ * `stream` is a cudaStream_t passed as void*. */
+int cufinufft_set_stream(cufinufft_plan plan, void *stream);
+int cufinufftf_set_stream(cufinufftf_plan plan, void *stream);
+
+/* Host-buffer convenience: same as setpts/execute but x,y,z / c,fk are HOST pointers
+ * (pinned or pageable); copies are issued on the plan's stream and execute_host returns
+ * after the result is back in host memory. */
+int cufinufft_setpts_host(int M, const double *x, const double *y, const double *z, cufinufft_plan plan);
+int cufinufftf_setpts_host(int M, const float *x, const float *y, const float *z, cufinufftf_plan plan);
+int cufinufft_execute_host(cuDoubleComplex *c, cuDoubleComplex *fk, cufinufft_plan plan);
+int cufinufftf_execute_host(cuFloatComplex *c, cuFloatComplex *fk, cufinufftf_plan plan);
+
+/* Stage-level calls on a plan that has points set (device pointers):
+ *   spread:  fw[ntransf-batch][nf3][nf2][nf1] = sum_j c_j phi(.)   (fw is zeroed first)
+ *   interp:  c_j = sum fw phi(.)
+ * `nt` transforms are processed (c stride M, fw stride nf1*nf2*nf3). */
+int cufinufft_spread(cuDoubleComplex *c, cuDoubleComplex *fw, int nt, cufinufft_plan plan);
+int cufinufftf_spread(cuFloatComplex *c, cuFloatComplex *fw, int nt, cufinufftf_plan plan);
+int cufinufft_interp(cuDoubleComplex *c, cuDoubleComplex *fw, int nt, cufinufft_plan plan);
+int cufinufftf_interp(cuFloatComplex *c, cuFloatComplex *fw, int nt, cufinufftf_plan plan);
+
+/* Introspection.  `what` selects the quantity; ints are written to out[0..]:
+ *   geometry (host): 0 -> {dim, nf1, nf2, nf3, ns, nbins1, nbins2, nbins3, binsx, binsy, binsz,
+ *                          maxbatchsize, M, totalnumsubprob, method, nbins_total}
+ * device arrays copied to the HOST buffer `out` (caller sizes it from the geometry):
+ *   1 binsize[nbins]  2 binstartpts[nbins]  3 numsubprob[nbins]  4 subprobstartpts[nbins+1]
+ *   5 subprob_to_bin[totalnumsubprob]  6 idxnupts[M]                                          */
+int cufinufft_get_ints(cufinufft_plan plan, int what, int *out);
+int cufinufftf_get_ints(cufinufftf_plan plan, int what, int *out);
+/* fwkerhalf (phihat) of dimension d=0,1,2: nf_d/2+1 reals to HOST buffer out; kernel params:
+ * d=-1 -> {beta, c, halfwidth} */
+int cufinufft_get_reals(cufinufft_plan plan, int d, double *out);
+int cufinufftf_get_reals(cufinufftf_plan plan, int d, float *out);
+
+/* Device time (ms) of the stages of the LAST execute (synchronises the stream):
+ * out[0]=spread|interp, out[1]=fft, out[2]=deconvolve|amplify, out[3]=memset, out[4]=total.
+ * Timing is recorded only after cufinufft*_set_timing(plan, 1). */
+int cufinufft_set_timing(cufinufft_plan plan, int on);
+int cufinufftf_set_timing(cufinufftf_plan plan, int on);
+int cufinufft_get_timing(cufinufft_plan plan, float *out);
+int cufinufftf_get_timing(cufinufftf_plan plan, float *out);
+/* number of kernels this library launched in the last setpts / execute (bench.py's gpu_launches) */
+int cufinufft_get_launch_counts(cufinufft_plan plan, int *out2);
+int cufinufftf_get_launch_counts(cufinufftf_plan plan, int *out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

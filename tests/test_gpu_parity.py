@@ -1,0 +1,91 @@
+"""GPU parity tests: our CUDA path (through the C ABI / Python class) against the CPU
+oracle on identical seeded inputs.  Tolerances: BASELINE.json north_star -- bin counts and
+offsets bit-exact; transforms rel-l2 <= 1e-5 (fp32) / 1e-12 (fp64) against the reference
+arithmetic; outputs within the requested tol of direct sums."""
+import numpy as np
+import pytest
+
+from helpers import cdtype, gpu_nufft, make_modes_data, make_points, make_strengths, rel_l2
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_PARITY = {np.float32: 1e-5, np.float64: 1e-12}
+
+
+def _check_bins(plan, pts, dtype, maxsub=1024):
+    lay = plan.bin_layout()
+    dim = len(pts)
+    nf = [lay["nf1"], lay["nf2"], lay["nf3"]][:dim]
+    bs = [lay["binsx"], lay["binsy"], lay["binsz"]][:dim]
+    ref = orc.binsort(pts, nf, bs, maxsub)
+    for key in ("binsize", "binstartpts", "numsubprob", "subprobstartpts", "subprob_to_bin"):
+        assert np.array_equal(lay[key], ref[key]), key
+    assert lay["totalnumsubprob"] == ref["totalnumsubprob"]
+    # idxnupts: a permutation, bin-major, equal to the oracle's as per-bin sets
+    idx, M = lay["idxnupts"], pts[0].size
+    assert np.array_equal(np.sort(idx), np.arange(M))
+    starts = ref["binstartpts"]
+    ours = np.sort(idx[: M]) if M == 0 else None
+    for b in np.flatnonzero(ref["binsize"])[:: max(1, len(starts) // 200)]:
+        s, n = starts[b], ref["binsize"][b]
+        assert np.array_equal(np.sort(idx[s:s + n]), np.sort(ref["idxnupts"][s:s + n]))
+
+
+CASES = [
+    # (type, modes, M, tol, dtype, opts)
+    (1, (64, 48), 20000, 1e-4, np.float32, {}),
+    (2, (64, 48), 20000, 1e-4, np.float32, {}),
+    (1, (100, 80), 30000, 1e-3, np.float32, {}),                       # config-1 shape (ns=4), nf not a bin multiple
+    (1, (40, 36), 5000, 1e-6, np.float32, {}),
+    (1, (64, 48), 20000, 1e-9, np.float64, {}),
+    (2, (64, 48), 20000, 1e-9, np.float64, {}),                        # config-2 shape (ns=10, GM-sort interp)
+    (1, (64, 48), 20000, 1e-4, np.float32, dict(gpu_method=1)),
+    (1, (64, 48), 20000, 1e-4, np.float32, dict(gpu_method=1, gpu_sort=0)),
+    (2, (64, 48), 20000, 1e-4, np.float32, dict(gpu_method=2)),
+    (1, (24, 20, 16), 20000, 1e-5, np.float32, {}),                    # config-3 shape (ns=6, SM 3-D)
+    (2, (24, 20, 16), 20000, 1e-5, np.float32, {}),
+    (1, (24, 20, 16), 20000, 1e-5, np.float32, dict(gpu_method=4)),
+    (1, (20, 18, 16), 8000, 1e-9, np.float64, {}),
+    (2, (20, 18, 16), 8000, 1e-9, np.float64, {}),                     # config-5 shape (ns=10, 3-D fp64)
+    (1, (200,), 5000, 1e-5, np.float32, {}),
+    (2, (200,), 5000, 1e-5, np.float32, {}),
+    (1, (200,), 5000, 1e-10, np.float64, {}),
+    (2, (200,), 5000, 1e-10, np.float64, {}),
+    (1, (8, 8), 100, 1e-3, np.float32, {}),                            # nf=16 < bin 32 ("make check" 8x8 cases)
+    (1, (8, 8, 8), 32, 1e-3, np.float32, dict(gpu_sort=0, gpu_maxsubprobsize=10)),   # reference test_opts
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "t%d-%s-M%d-%g-%s-%s" % (
+    c[0], "x".join(map(str, c[1])), c[2], c[3], np.dtype(c[4]).name, "_".join("%s%s" % kv for kv in c[5].items())))
+def test_transform_vs_oracle(case):
+    nufft_type, modes, M, tol, dtype, opts = case
+    dim = len(modes)
+    pts = make_points(M, dim, dtype, seed=10 + dim)
+    if nufft_type == 1:
+        data = make_strengths(M, dtype)
+    else:
+        data = make_modes_data(modes, dtype)
+    out, plan = gpu_nufft(nufft_type, modes, pts, data, tol, dtype, return_plan=True, **opts)
+    ref = orc.nufft(nufft_type, modes, pts, data[0], tol, dtype=dtype)
+    err = rel_l2(out[0], ref)
+    assert err <= TOL_PARITY[dtype], err
+    if plan.geometry()["method"] == 2 or opts.get("gpu_sort", 1):
+        if opts.get("gpu_method", 0) != 4:
+            _check_bins(plan, pts, dtype, opts.get("gpu_maxsubprobsize", 1024))
+    # accuracy against the direct sum at sampled outputs (<= requested tol, with the usual
+    # factor for the l2 -> sampled max conversion)
+    rng = np.random.default_rng(5)
+    if nufft_type == 1:
+        idx = rng.integers(0, int(np.prod(modes)), 50)
+        exact = orc.dirft1_sampled(pts, data[0], modes, 1, idx)
+        got = out[0].ravel()[idx]
+        scale = np.abs(exact).max()
+    else:
+        idx = rng.integers(0, M, 50)
+        exact = orc.dirft2_sampled(pts, data[0], modes, -1, idx)
+        got = out[0][idx]
+        scale = np.abs(exact).max()
+    floor = 3e-6 if dtype == np.float32 else 1e-13
+    assert np.abs(got - exact).max() / scale <= max(10 * tol, floor)
