@@ -248,8 +248,7 @@ static int execute(Plan<T> *p, typename Plan<T>::C *c, typename Plan<T>::C *fk)
             if (int e = stage_interp(*p, cb, fw, nt)) return e;
             mark(4);
         }
-        p->launches_exec++;                      // the cuFFT call (library kernels, counted once)
-    }
+    }                                            // launches_exec counts OUR kernels only (cuFFT's are not)
     return 0;
 }
 
