@@ -18,7 +18,13 @@ namespace cfb {
 
 struct DeviceGuard {            // every API call runs on opts.gpu_device_id and restores the
     int prev = 0;               // caller's device (reference src/cufinufft.cu:101-110,270)
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); target = dev; }
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (dev != prev) cudaSetDevice(dev);
+        target = dev;
+        cudaGetLastError();     // do not inherit a stale non-sticky error left by other code in the process
+    }
     ~DeviceGuard() { if (target != prev) cudaSetDevice(prev); }
     int target = 0;
 };

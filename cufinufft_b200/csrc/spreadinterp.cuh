@@ -158,27 +158,38 @@ spread_sm_kernel(const SIArgs<T> a)
                 s_off[lane] = off;
             }
             __syncwarp();
+            // lane-per-cell accumulation.  All loads of a chunk of passes (weights + tile cells)
+            // are issued before any store so they overlap (the compiler must otherwise assume
+            // the tile store of one pass aliases the loads of the next), and the next point's
+            // header is fetched before this point's stores.
+            int off_n = s_off[0];
+            T k1_n = s_ker[ix], cr_n = s_cre[0], ci_n = s_cim[0];
             for (int q = 0; q < cnt; ++q) {
-                if (active) {
-                    const T *kq = s_ker + q * G::KVP;
-                    const T k1 = kq[ix];
-                    const T cr = s_cre[q] * k1, ci = s_cim[q] * k1;
-                    C *cell0 = tile + s_off[q] + ix;
+                const T *kq = s_ker + q * G::KVP;
+                const T cr = cr_n * k1_n, ci = ci_n * k1_n;
+                C *cell0 = tile + off_n + ix;
+                const int qn = q + 1 < cnt ? q + 1 : q;
+                off_n = s_off[qn]; k1_n = s_ker[qn * G::KVP + ix]; cr_n = s_cre[qn]; ci_n = s_cim[qn];
+                constexpr int CH = G::ITERS < 8 ? G::ITERS : 8;
+#pragma unroll(G::ITERS <= 16 ? 16 : 1)
+                for (int it0 = 0; it0 < G::ITERS; it0 += CH) {
+                    C v[CH]; T wgt[CH]; int toff[CH]; bool ok[CH];
 #pragma unroll
-                    for (int it = 0; it < G::ITERS; ++it) {
-                        const int row = it * G::R + r;
-                        if (row < G::ROWS) {
-                            T wgt; int toff;
-                            if (DIM == 1) { wgt = 1; toff = 0; }
-                            else if (DIM == 2) { wgt = kq[NS + row]; toff = row * a.sy; }
-                            else { const int iz = row / NS, iy = row - iz * NS;
-                                   wgt = kq[NS + iy] * kq[2 * NS + iz]; toff = iz * a.sz + iy * a.sy; }
-                            C v = cell0[toff];
-                            v.x = fma(cr, wgt, v.x);
-                            v.y = fma(ci, wgt, v.y);
-                            cell0[toff] = v;
-                        }
+                    for (int j = 0; j < CH; ++j) {
+                        const int row = (it0 + j) * G::R + r;
+                        ok[j] = active && row < G::ROWS && (it0 + j) < G::ITERS;
+                        if (DIM == 1) { wgt[j] = 1; toff[j] = 0; }
+                        else if (DIM == 2) { toff[j] = row * a.sy; wgt[j] = ok[j] ? kq[NS + row] : (T)0; }
+                        else { const int iz = row / NS, iy = row - iz * NS;
+                               toff[j] = iz * a.sz + iy * a.sy;
+                               wgt[j] = ok[j] ? kq[NS + iy] * kq[2 * NS + iz] : (T)0; }
                     }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) { if (ok[j]) v[j] = cell0[toff[j]]; else { v[j].x = 0; v[j].y = 0; } }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) { v[j].x = fma(cr, wgt[j], v[j].x); v[j].y = fma(ci, wgt[j], v[j].y); }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) if (ok[j]) cell0[toff[j]] = v[j];
                 }
                 __syncwarp();
             }
@@ -276,10 +287,39 @@ spread_gm_kernel(const SIArgs<T> a)
 }
 
 // =============================================================================
-// Interpolation: warp per point, lanes over the stencil, coalesced row gathers from
-// the fine grid (L2/L1; points are bin-ordered so neighbouring points reuse lines),
-// butterfly reduction, result scattered to c[idxnupts].
+// Interpolation: warp per point, lanes over the stencil (lane = (row r, column ix)),
+// coalesced row gathers from the fine grid (L1/L2: points are bin-ordered so neighbouring
+// points reuse lines).  Each lane accumulates its column over the passes with the row
+// weights only (2 FMA per cell), scales by its x-weight once, and the 32 partial sums of
+// EIGHT points are reduced together by a transposing butterfly (9 shuffles per component
+// per 8 points instead of 40).  Result scattered to c[idxnupts].
 // =============================================================================
+template <typename T>
+__device__ __forceinline__ T reduce8(T (&v)[8], int lane)
+{
+    // after the call every lane holds the full sum of point  4*bit4 + 2*bit3 + bit2  of its lane id
+    bool up = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        T send = up ? v[j] : v[j + 4], keep = up ? v[j + 4] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    up = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        T send = up ? v[j] : v[j + 2], keep = up ? v[j + 2] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    up = lane & 4;
+    {
+        T send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
 template <typename T, int DIM, int NS>
 __global__ void __launch_bounds__(256)
 interp_kernel(const SIArgs<T> a)
@@ -290,11 +330,12 @@ interp_kernel(const SIArgs<T> a)
     T *s_hc = reinterpret_cast<T *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char *wbase = smem + 18 * 16 * sizeof(T) + warp * (warp_scratch_bytes<T, DIM, NS>() + 2 * 32 * sizeof(int));
-    T *s_cre = reinterpret_cast<T *>(wbase);
+    T *s_cre = reinterpret_cast<T *>(wbase);          // unused by interp (kept for the common layout)
     T *s_cim = s_cre + 32;
     T *s_ker = s_cim + 32;
     int *s_x0 = reinterpret_cast<int *>(s_ker + 32 * G::KVP);
     int *s_y0 = s_x0 + 32, *s_z0 = s_y0 + 32;
+    int *s_idx = reinterpret_cast<int *>(s_cre);      // idxnupts of the 32 points of the batch
     stage_horner<T, NS>(a, s_hc);
 
     const int r = lane / NS, ix = lane - r * NS;
@@ -302,6 +343,7 @@ interp_kernel(const SIArgs<T> a)
     const long long nbatch = ((long long)a.M + 31) / 32;
     const long long total = nbatch * a.nt;
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    const size_t plane = (size_t)a.nf1 * a.nf2;
 
     for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp; w < total; w += wstride) {
         const int t = (int)(w / nbatch);
@@ -309,47 +351,53 @@ interp_kernel(const SIArgs<T> a)
         const int cnt = (int)min((long long)32, a.M - pb);
         C *cout = a.c + (size_t)t * a.M;
         const C *fwt = a.fw + (size_t)t * a.fwstride;
-        int myidx = 0;
         if (lane < cnt) {
             const int p = (int)(pb + lane);
             int xs0, ys0 = 0, zs0 = 0;
             point_weights<T, DIM, NS>(a, p, s_ker + lane * G::KVP, s_hc, xs0, ys0, zs0);
-            myidx = a.idx[p];
-            s_x0[lane] = xs0; s_y0[lane] = ys0; s_z0[lane] = zs0;
+            s_idx[lane] = a.idx[p];
+            s_x0[lane] = clampi(xs0, -a.nf1, a.nf1);
+            s_y0[lane] = clampi(ys0, -a.nf2, a.nf2);
+            s_z0[lane] = clampi(zs0, -a.nf3, a.nf3);
         }
         __syncwarp();
-        T out_re = 0, out_im = 0;
-        for (int q = 0; q < cnt; ++q) {
-            T accr = 0, acci = 0;
-            if (active) {
-                const T *kq = s_ker + q * G::KVP;
-                const T k1 = kq[ix];
-                const int gx = wrap_index(clampi(s_x0[q], -a.nf1, a.nf1) + ix, a.nf1);
-                const int y0 = clampi(s_y0[q], -a.nf2, a.nf2), z0 = clampi(s_z0[q], -a.nf3, a.nf3);
+        for (int q0 = 0; q0 < cnt; q0 += 8) {
+            T accr[8], acci[8];
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it) {
-                    const int row = it * G::R + r;
-                    if (row < G::ROWS) {
-                        T wgt = k1; size_t o = gx;
-                        if (DIM == 2) { wgt *= kq[NS + row]; o += (size_t)wrap_index(y0 + row, a.nf2) * a.nf1; }
-                        if (DIM == 3) { const int iz = row / NS, iy = row - iz * NS;
-                                        wgt *= kq[NS + iy] * kq[2 * NS + iz];
-                                        o += (size_t)wrap_index(y0 + iy, a.nf2) * a.nf1 +
-                                             (size_t)wrap_index(z0 + iz, a.nf3) * a.nf1 * a.nf2; }
-                        const C v = fwt[o];
-                        accr = fma(v.x, wgt, accr);
-                        acci = fma(v.y, wgt, acci);
+            for (int j = 0; j < 8; ++j) {
+                accr[j] = 0; acci[j] = 0;
+                const int q = q0 + j;
+                if (active && q < cnt) {
+                    const T *kq = s_ker + q * G::KVP;
+                    const C *col = fwt + wrap_index(s_x0[q] + ix, a.nf1);
+                    const int y0 = s_y0[q], z0 = s_z0[q];
+                    T sr = 0, si = 0;
+#pragma unroll(G::ITERS <= 12 ? 12 : 4)
+                    for (int it = 0; it < G::ITERS; ++it) {
+                        const int row = it * G::R + r;
+                        if (row < G::ROWS) {
+                            T wgt; size_t o;
+                            if (DIM == 1) { wgt = 1; o = 0; }
+                            else if (DIM == 2) { wgt = kq[NS + row]; o = (size_t)wrap_index(y0 + row, a.nf2) * a.nf1; }
+                            else { const int iz = row / NS, iy = row - iz * NS;
+                                   wgt = kq[NS + iy] * kq[2 * NS + iz];
+                                   o = (size_t)wrap_index(y0 + iy, a.nf2) * a.nf1 + (size_t)wrap_index(z0 + iz, a.nf3) * plane; }
+                            const C v = col[o];
+                            sr = fma(v.x, wgt, sr);
+                            si = fma(v.y, wgt, si);
+                        }
                     }
+                    const T k1 = kq[ix];
+                    accr[j] = sr * k1; acci[j] = si * k1;
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                accr += __shfl_xor_sync(0xffffffffu, accr, o);
-                acci += __shfl_xor_sync(0xffffffffu, acci, o);
-            }
-            if (lane == q) { out_re = accr; out_im = acci; }
+            const T tr = reduce8(accr, lane), ti = reduce8(acci, lane);
+            const int q = q0 + ((lane >> 2) & 7);
+            // lane bits (4,3,2) select the point in reduce8's order: 4*bit4 + 2*bit3 + bit2
+            const int qsel = q0 + (((lane >> 4) & 1) << 2) + (((lane >> 3) & 1) << 1) + ((lane >> 2) & 1);
+            (void)q;
+            if ((lane & 3) == 0 && qsel < cnt) { C o; o.x = tr; o.y = ti; cout[s_idx[qsel]] = o; }
         }
-        if (lane < cnt) { C v; v.x = out_re; v.y = out_im; cout[myidx] = v; }
         __syncwarp();
     }
 }

@@ -66,3 +66,22 @@ def gpu_nufft(nufft_type, modes, pts, data, tol, dtype, ntransf=1, maxbatch=1, i
     if return_plan:
         return out, plan
     return out
+
+
+def drop_exact_stencil_points(pts, nf, ns):
+    """Remove points whose rescaled coordinate makes `x_r - ns/2` an exact integer in any
+    dimension.  For those the reference loops over ns+1 stencil points and reads ker[ns],
+    an UNINITIALISED local (src/2d/spreadinterp2d.cu:35-38 with src/cuspreadinterp.h:37;
+    SURVEY.md A.1), so its own output is garbage there (measured: such points alone move its
+    result by up to 2e-3 rel-l2 and it is then further from the direct sum than ours).
+    Parity against the reference library is therefore asserted on inputs without them.
+    Rescale as contrib/spreadinterp.h:36-38 (double arithmetic, narrowed to the real type)."""
+    dtype = pts[0].dtype.type
+    keep = np.ones(pts[0].size, bool)
+    pi = dtype(np.pi)
+    for d, x in enumerate(pts):
+        shift = np.where(x < -pi, 1.5, np.where(x >= pi, -0.5, 0.5))
+        xr = ((x.astype(np.float64) * 0.159154943091895336 + shift) * nf[d]).astype(dtype).astype(np.float64)
+        t = xr - ns / 2.0
+        keep &= np.ceil(t) != t
+    return [np.ascontiguousarray(p[keep]) for p in pts]

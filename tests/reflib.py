@@ -86,9 +86,11 @@ class RefPlan:
         g = self.geometry()
         out = dict(g)
         f = self._fn("refg_get_ints%s", [c_void_p, c_int, c_void_p])
-        for name, what, n in (("binsize", 1, g["nbins"]), ("binstartpts", 2, g["nbins"]), ("numsubprob", 3, g["nbins"]),
-                              ("subprobstartpts", 4, g["nbins"] + 1), ("subprob_to_bin", 5, g["totalnumsubprob"]),
-                              ("idxnupts", 6, g["M"])):
+        wanted = [("binsize", 1, g["nbins"]), ("binstartpts", 2, g["nbins"]), ("idxnupts", 6, g["M"])]
+        if g["method"] == 2:      # the reference allocates the subproblem arrays only for the SM method
+            wanted += [("numsubprob", 3, g["nbins"]), ("subprobstartpts", 4, g["nbins"] + 1),
+                       ("subprob_to_bin", 5, g["totalnumsubprob"])]
+        for name, what, n in wanted:
             arr = np.zeros(max(n, 1), np.int32)
             assert f(self.plan, what, arr.ctypes.data_as(c_void_p)) == 0, name
             out[name] = arr[:n]
