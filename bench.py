@@ -218,7 +218,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--scale", type=float, default=1.0, help="scale M (debug)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -324,6 +324,8 @@ def main():
     # ---- end-to-end: host (pinned) buffers through the host C-ABI call ----
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         c_host = torch.empty((ntransf, M), dtype=cdt, pin_memory=True)
         fk_host = torch.empty((ntransf,) + shape, dtype=cdt, pin_memory=True)
         c_host.copy_(c)

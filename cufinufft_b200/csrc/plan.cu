@@ -86,49 +86,38 @@ static void free_plan(Plan<T> *p)
     delete p;
 }
 
+// Host-only part of makeplan (no CUDA call): validates the arguments and derives every
+// plan-time number -- kernel width/beta, fine grid, bin grid, batch size, engine choice.
+// Reference: src/cufinufft.cu:118-175 (+ SETUP_BINSIZE :17-73, spread wrappers' numbins).
 template <typename T>
-static int makeplan(int type, int dim, int *nmodes, int iflag, int ntransf, T tol, int maxbatchsize,
-                    Plan<T> **out, cufinufft_opts *user_opts)
+static int plan_host_setup(Plan<T> *p, int type, int dim, const int *nmodes, int iflag, int ntransf, T tol,
+                           int maxbatchsize, const cufinufft_opts *user_opts)
 {
-    if (!out) return CFB_ERR_BAD_ARG;
-    *out = nullptr;
     if (!nmodes || dim < 1 || dim > 3 || ntransf < 1) return CFB_ERR_BAD_ARG;
     if (type == 3) { fprintf(stderr, "[cufinufft-b200] type 3: Not Implemented yet\n"); return CFB_ERR_NOT_IMPLEMENTED; }
     if (type != 1 && type != 2) return CFB_ERR_BAD_ARG;
-
-    Plan<T> *p = new (std::nothrow) Plan<T>();
-    if (!p) return CFB_ERR_BAD_ARG;
     if (user_opts) p->opts = *user_opts;
     else default_opts(type, dim, &p->opts);
     p->device = p->opts.gpu_device_id;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
-        fprintf(stderr, "[cufinufft-b200] no CUDA device available: this library has no CPU fallback\n");
-        delete p;
-        return CFB_ERR_CUDA;
-    }
-    if (p->device < 0 || p->device >= ndev) { delete p; return CFB_ERR_BAD_ARG; }
-    DeviceGuard guard(p->device);
 
     int ier = setup_spreader<T>(tol, p->opts.upsampfac, p->opts.gpu_kerevalmeth, &p->ns, &p->es_beta, &p->es_halfwidth, &p->es_c);
-    if (ier > 1) { delete p; return ier; }
+    if (ier > 1) return ier;
 
     p->type = type; p->dim = dim;
     p->ms = nmodes[0];
     p->mt = dim > 1 ? nmodes[1] : 1;
     p->mu = dim > 2 ? nmodes[2] : 1;
-    if (p->ms < 1 || p->mt < 1 || p->mu < 1) { delete p; return CFB_ERR_BAD_ARG; }
+    if (p->ms < 1 || p->mt < 1 || p->mu < 1) return CFB_ERR_BAD_ARG;
     int m = p->opts.gpu_method;
     if (m < 1 || m > 4 || (m == 3 && dim != 2) || (m == 4 && dim != 3)) {
         fprintf(stderr, "[cufinufft-b200] invalid gpu_method %d for dim %d\n", m, dim);
-        delete p;
         return CFB_ERR_BAD_ARG;
     }
     setup_binsize(dim, &p->opts);
     p->nf1 = set_nf_type12(p->ms, p->opts.upsampfac, p->ns, m, p->opts.gpu_obinsizex);
     if (dim > 1) p->nf2 = set_nf_type12(p->mt, p->opts.upsampfac, p->ns, m, p->opts.gpu_obinsizey);
     if (dim > 2) p->nf3 = set_nf_type12(p->mu, p->opts.upsampfac, p->ns, m, p->opts.gpu_obinsizez);
-    if ((double)p->nf1 * p->nf2 * p->nf3 > 2147483647.0) { delete p; return CFB_ERR_BAD_ARG; }   // int32 cells, as the reference
+    if ((double)p->nf1 * p->nf2 * p->nf3 > 2147483647.0) return CFB_ERR_BAD_ARG;   // int32 cells, as the reference
     p->iflag = iflag >= 0 ? 1 : -1;
     p->ntransf = ntransf;
     if (maxbatchsize <= 0) maxbatchsize = ntransf < 8 ? ntransf : 8;     // reference heuristic, :167-168
@@ -142,14 +131,35 @@ static int makeplan(int type, int dim, int *nmodes, int iflag, int ntransf, T to
     p->bs[0] = p->opts.gpu_binsizex; p->bs[1] = dim > 1 ? p->opts.gpu_binsizey : 1; p->bs[2] = dim > 2 ? p->opts.gpu_binsizez : 1;
     if (m == 4) { p->bs[0] = p->opts.gpu_obinsizex; p->bs[1] = p->opts.gpu_obinsizey; p->bs[2] = p->opts.gpu_obinsizez; }
     for (int d = 0; d < dim; ++d)
-        if (p->bs[d] < 1) { fprintf(stderr, "[cufinufft-b200] invalid bin size\n"); delete p; return CFB_ERR_BAD_ARG; }
-    if (p->opts.gpu_maxsubprobsize < 1) { delete p; return CFB_ERR_BAD_ARG; }
+        if (p->bs[d] < 1) { fprintf(stderr, "[cufinufft-b200] invalid bin size\n"); return CFB_ERR_BAD_ARG; }
+    if (p->opts.gpu_maxsubprobsize < 1) return CFB_ERR_BAD_ARG;
     const int nf[3] = {p->nf1, p->nf2, p->nf3};
     p->nbins = 1;
     for (int d = 0; d < 3; ++d) {
         p->nbin[d] = d < dim ? (int)ceil((T)nf[d] / p->bs[d]) : 1;       // numbins = ceil((FLT)nf/bin), spread2d_wrapper.cu:405-406
         p->nbins *= p->nbin[d];
     }
+    return 0;
+}
+
+template <typename T>
+static int makeplan(int type, int dim, int *nmodes, int iflag, int ntransf, T tol, int maxbatchsize,
+                    Plan<T> **out, cufinufft_opts *user_opts)
+{
+    if (!out) return CFB_ERR_BAD_ARG;
+    *out = nullptr;
+    Plan<T> *p = new (std::nothrow) Plan<T>();
+    if (!p) return CFB_ERR_BAD_ARG;
+    if (int ier = plan_host_setup<T>(p, type, dim, nmodes, iflag, ntransf, tol, maxbatchsize, user_opts)) { delete p; return ier; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        fprintf(stderr, "[cufinufft-b200] no CUDA device available: this library has no CPU fallback\n");
+        delete p;
+        return CFB_ERR_CUDA;
+    }
+    if (p->device < 0 || p->device >= ndev) { delete p; return CFB_ERR_BAD_ARG; }
+    DeviceGuard guard(p->device);
+    const int nf[3] = {p->nf1, p->nf2, p->nf3};
 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) { delete p; return CFB_ERR_CUDA; }
@@ -364,6 +374,20 @@ static int get_timing(Plan<T> *p, float *out)
     return 0;
 }
 
+// plan-time numbers without a device (tests of the host logic run where no GPU exists)
+template <typename T>
+static int host_params(int type, int dim, const int *nmodes, double tol, const cufinufft_opts *opts, int *oi, double *od)
+{
+    Plan<T> p;
+    int ier = plan_host_setup<T>(&p, type, dim, nmodes, 1, 1, (T)tol, 1, opts);
+    if (ier) return ier;
+    const int v[16] = {p.ns, p.nf1, p.nf2, p.nf3, p.bs[0], p.bs[1], p.bs[2], p.nbin[0], p.nbin[1], p.nbin[2], p.nbins,
+                       p.method, p.sorted ? 1 : 0, p.maxbatch, p.opts.gpu_method, (int)(2 + 3.0 * (T)(p.ns / 2.0))};
+    memcpy(oi, v, sizeof(v));
+    od[0] = (double)p.es_beta; od[1] = (double)p.es_c; od[2] = (double)p.es_halfwidth;
+    return 0;
+}
+
 template <typename T>
 static int stage_only(Plan<T> *p, typename Plan<T>::C *c, typename Plan<T>::C *fw, int nt, bool spread)
 {
@@ -390,6 +414,22 @@ struct cufinufftf_plan_s { Plan<float> *p;  cfb::DevBuf dc, dfk; };
 extern "C" {
 
 const char *cufinufft_b200_version(void) { return "cufinufft-b200 0.1 (API of cuFINUFFT 1.3)"; }
+
+int cufinufft_b200_host_params(int type, int dim, const int *nmodes, double tol, int single_precision,
+                               const cufinufft_opts *opts, int *out_ints16, double *out_reals3)
+{
+    if (!out_ints16 || !out_reals3) return CFB_ERR_BAD_ARG;
+    return single_precision ? cfb::host_params<float>(type, dim, nmodes, tol, opts, out_ints16, out_reals3)
+                            : cfb::host_params<double>(type, dim, nmodes, tol, opts, out_ints16, out_reals3);
+}
+int cufinufft_b200_phihat_quadrature(int nf, int ns, double beta, double es_c, double halfwidth, int single_precision,
+                                     void *f, double *a_reim)
+{
+    if (!f || !a_reim || ns < 2 || ns > cfb::MAX_NS || nf < 2) return CFB_ERR_BAD_ARG;
+    if (single_precision) cfb::fseries_precomp<float>(nf, ns, (float)beta, (float)es_c, (float)halfwidth, (float *)f, a_reim);
+    else cfb::fseries_precomp<double>(nf, ns, beta, es_c, halfwidth, (double *)f, a_reim);
+    return 0;
+}
 
 int cufinufft_default_opts(int type, int dim, cufinufft_opts *opts) { return cfb::default_opts(type, dim, opts); }
 int cufinufftf_default_opts(int type, int dim, cufinufft_opts *opts) { return cfb::default_opts(type, dim, opts); }

@@ -38,6 +38,20 @@ enum {
 
 const char *cufinufft_b200_version(void);
 
+/* Host-only views of the plan-time arithmetic (no CUDA call; usable without a device):
+ *  host_params: what makeplan derives from (type, dim, nmodes, tol, opts) --
+ *    out_ints16 = {ns, nf1, nf2, nf3, binsx, binsy, binsz, nbins1, nbins2, nbins3, nbins_total,
+ *                  engine (1 GM | 2 SM), sorted, maxbatchsize, gpu_method, nquad}
+ *    out_reals3 = {ES_beta, ES_c, ES_halfwidth}
+ *    (reference: setup_spreader contrib/spreadinterp.cpp:6-67, SET_NF_TYPE12 contrib/common.cpp:24-37,
+ *     SETUP_BINSIZE src/cufinufft.cu:17-73); opts may be NULL (defaults).
+ *  phihat_quadrature: the f[n] (float or double, by single_precision) and a[n] (re,im doubles)
+ *    of onedim_fseries_kernel_precomp, contrib/common.cpp:84-96. */
+int cufinufft_b200_host_params(int type, int dim, const int *nmodes, double tol, int single_precision,
+                               const cufinufft_opts *opts, int *out_ints16, double *out_reals3);
+int cufinufft_b200_phihat_quadrature(int nf, int ns, double beta, double es_c, double halfwidth, int single_precision,
+                                     void *f, double *a_reim);
+
 /* Stream on which all work of the plan is enqueued (default: the legacy default stream 0).
  * `stream` is a cudaStream_t passed as void*. */
 int cufinufft_set_stream(cufinufft_plan plan, void *stream);

@@ -215,6 +215,13 @@ static inline void ORC(kervec_horner)(FLT *ker, FLT x, int w)
     }
 }
 
+/* exported views for the pinning tests (tests/test_oracle_pinned.py) */
+void ORC(orc_horner_eval)(int w, FLT x1, FLT *ker) { ORC(kervec_horner)(ker, x1, w); }
+void ORC(orc_host_kernel_vec)(int n, const FLT *x, FLT beta, FLT c, FLT halfwidth, FLT *out)
+{
+    for (int i = 0; i < n; ++i) out[i] = ORC(host_kernel)(x[i], beta, c, halfwidth);
+}
+
 static inline int ORC(wrap)(int i, int nf) { return i < 0 ? i + nf : (i > nf - 1 ? i - nf : i); }
 
 /* stencil start + kernel vector for one coordinate:

@@ -251,6 +251,27 @@ def dirft2_sampled(pts, fk, modes, iflag, ptidx):
     return out
 
 
+def host_kernel(x, kp):
+    """evaluate_kernel of contrib/spreadinterp.cpp:69-81 on an array."""
+    s, FT = _sfx(kp.dtype)
+    x = np.ascontiguousarray(x, kp.dtype)
+    out = np.zeros(x.size, kp.dtype)
+    fn = getattr(lib, "orc_host_kernel_vec" + s)
+    fn.argtypes = [c_int, c_void_p, FT, FT, FT, c_void_p]
+    fn(x.size, _p(x), FT(kp.beta), FT(kp.c), FT(kp.halfwidth), _p(out))
+    return out
+
+
+def horner_eval(w, x1, dtype):
+    """ker[0..w-1] of eval_kernel_vec_Horner (src/cuspreadinterp.h:18-31) with OUR table."""
+    s, FT = _sfx(dtype)
+    out = np.zeros(16, dtype)
+    fn = getattr(lib, "orc_horner_eval" + s)
+    fn.argtypes = [c_int, FT, c_void_p]
+    fn(int(w), FT(x1), _p(out))
+    return out[:w]
+
+
 def horner_table(w):
     lib.orc_horner_table_export.restype = ctypes.POINTER(c_double)
     lib.orc_horner_ncoef_export.restype = c_int

@@ -61,6 +61,15 @@ void SFX(refh_dirft2d2)(int nj, FLT *x, FLT *y, FLT *c, int iflag, int ms, int m
     dirft2d2(nj, x, y, (CPX *)c, iflag, ms, mt, (CPX *)f);
 }
 
+/* the reference's generated piecewise-polynomial table, evaluated on the host exactly as
+ * eval_kernel_vec_Horner does on the device (src/cuspreadinterp.h:18-31): the table file is a
+ * code fragment that expects `w`, `z` and `ker` in scope. */
+void SFX(refh_horner)(int w, FLT x, FLT *ker)
+{
+    FLT z = 2 * x + w - 1.0;
+#include "ker_horner_allw_loop.c"
+}
+
 #ifndef SINGLE
 int refh_next235beven(int n, int b) { return next235beven(n, b); }
 int refh_set_nf(int ms, double upsampfac, int ns, int gpu_method, int obinsize)
