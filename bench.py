@@ -136,6 +136,20 @@ def device_points(cfg, M, seed, torch, dev):
     return [torch.from_numpy(p).to(dev) for p in pts]
 
 
+def drop_exact_stencil_points(pts, nf, ns, torch):
+    """Device twin of tests/helpers.drop_exact_stencil_points: removes the points for which the
+    REFERENCE reads an uninitialised kernel weight (x_r - ns/2 an exact integer) --
+    its output is then garbage, often NaN.  Used only where ours is compared WITH the reference."""
+    keep = torch.ones_like(pts[0], dtype=torch.bool)
+    pi = torch.tensor(np.pi, dtype=pts[0].dtype).item()
+    for d, x in enumerate(pts):
+        shift = torch.where(x < -pi, 1.5, torch.where(x >= pi, -0.5, 0.5)).to(torch.float64)
+        xr = ((x.to(torch.float64) * 0.159154943091895336 + shift) * nf[d]).to(x.dtype).to(torch.float64)
+        t = xr - ns / 2.0
+        keep &= torch.ceil(t) != t
+    return [p[keep].contiguous() for p in pts]
+
+
 class TArr:
     """torch tensor seen through the .ptr/.dtype/.size protocol of the Python binding."""
 

@@ -35,6 +35,34 @@ __device__ __forceinline__ int stencil_start(T xr, int ns)
     return (int)ceil((double)xr - ns * 0.5);
 }
 
+// Stencil-origin cell of a point inside its bin: (stencil_start - first possible start of the
+// bin), clamped to [0, nk).  Only a SORT KEY (points of one key share their stencil origin, up
+// to the clamped edge cases); results never depend on it.
+template <typename T>
+__device__ __forceinline__ int stencil_cell(T xr, int ns, int bin_origin, int nk)
+{
+    int k = stencil_start(xr, ns) - (bin_origin - ns / 2);
+    if (!(ns & 1)) k -= 1;          // even widths: origin changes at integers, k = 0 only for xr exactly on the bin edge
+    return k < 0 ? 0 : (k >= nk ? nk - 1 : k);
+}
+
+__device__ __forceinline__ int rec_index(const PtRec<float> &r) { return r.idx; }
+__device__ __forceinline__ int rec_index(const PtRec<double> &r) { return (int)r.idx; }
+
+__device__ __forceinline__ PtRec<float> load_rec(const PtRec<float> *p)
+{
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    PtRec<float> r; r.x = v.x; r.y = v.y; r.z = v.z; r.idx = __float_as_int(v.w);
+    return r;
+}
+__device__ __forceinline__ PtRec<double> load_rec(const PtRec<double> *p)
+{
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    PtRec<double> r; r.x = a.x; r.y = a.y; r.z = b.x; r.idx = __double_as_longlong(b.y);
+    return r;
+}
+
 // ---- exp(beta*sqrt(1 - c x^2)) for |x| < ns/2, un-normalised as in the reference
 // (src/cuspreadinterp.h:6-16).  fp64 plans evaluate in double (bit-compatible formula);
 // fp32 plans evaluate in fp32 (the reference promotes to double here; our deviation is

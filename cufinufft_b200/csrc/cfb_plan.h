@@ -36,6 +36,21 @@ struct DevBuf {
     template <typename U> U *as() const { return static_cast<U *>(p); }
 };
 
+// One sorted point: rescaled coordinates (fine-grid units) + the point's index in the caller's
+// arrays.  16 bytes (fp32) / 32 bytes (fp64): one vector load per point in spread / interp and
+// one sector-sized scattered store per point in setpts.
+template <typename T> struct PtRec;
+template <> struct alignas(16) PtRec<float>  { float x, y, z; int idx; };
+template <> struct alignas(32) PtRec<double> { double x, y, z; long long idx; };
+
+// geometry of the setpts sort key: bin grid and the stencil-cell grid inside a bin
+struct SortGeo {
+    int nf[3], bs[3], nb[3];
+    int nk[3];      // distinct stencil origins per bin and dimension (1 = key is the bin alone)
+    int cpb;        // nk[0]*nk[1]*nk[2]
+    int ns;
+};
+
 template <typename T>
 struct Plan {
     using C = typename cplx_of<T>::type;
@@ -57,8 +72,12 @@ struct Plan {
     // points (borrowed) + derived (owned)
     int M = -1;
     const T *kx = nullptr, *ky = nullptr, *kz = nullptr;
-    DevBuf xs, ys, zs;                   // bin-ordered rescaled coordinates (grid units), T[M]
-    DevBuf sortidx, idxnupts;            // int[M]
+    DevBuf recs;                         // PtRec<T>[M], sorted by (bin, stencil cell)
+    DevBuf sortidx, idxnupts;            // int[M]: rank of a point inside its key; inverse permutation (on demand)
+    DevBuf keyoff, tilesum;              // int[nkeys+1] key histogram -> offsets; scan scratch
+    SortGeo sortgeo;
+    bool fine_sort_allowed = true;
+    bool idx_valid = false;
     DevBuf binsize, binstartpts, numsubprob, subprobstartpts, subprob_to_bin;
     DevBuf scalars;                      // int[8]: [0] totalnumsubprob, [1] work counter, ...
     DevBuf fw;                           // C[maxbatch * nf1*nf2*nf3]
@@ -98,6 +117,7 @@ void fseries_precomp(int nf, int ns, T beta, T es_c, T halfwidth, T *f, double *
 // ---- device stages ----------------------------------------------------------
 template <typename T> int stage_fseries(Plan<T> &p);                       // deconv.cu
 template <typename T> int stage_setpts(Plan<T> &p);                        // setpts.cu
+template <typename T> int materialize_idxnupts(Plan<T> &p);                // setpts.cu
 template <typename T> int stage_spread(Plan<T> &p, const typename Plan<T>::C *c, typename Plan<T>::C *fw, int nt);
 template <typename T> int stage_interp(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *fw, int nt);
 template <typename T> int stage_deconvolve(Plan<T> &p, typename Plan<T>::C *fk, const typename Plan<T>::C *fw, int nt);

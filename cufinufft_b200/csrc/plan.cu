@@ -78,7 +78,7 @@ static void free_plan(Plan<T> *p)
 {
     if (!p) return;
     if (p->have_fft) cufftDestroy(p->fftplan);
-    for (DevBuf *b : {&p->xs, &p->ys, &p->zs, &p->sortidx, &p->idxnupts, &p->binsize, &p->binstartpts, &p->numsubprob,
+    for (DevBuf *b : {&p->recs, &p->keyoff, &p->tilesum, &p->sortidx, &p->idxnupts, &p->binsize, &p->binstartpts, &p->numsubprob,
                       &p->subprobstartpts, &p->subprob_to_bin, &p->scalars, &p->fw, &p->fwker[0], &p->fwker[1],
                       &p->fwker[2], &p->hostside, &p->hcoef})
         b->release();
@@ -336,7 +336,11 @@ static int get_ints(Plan<T> *p, int what, int *out)
         case 3: CFB_CUDA_OK(d2h(p->numsubprob, nb)); return 0;
         case 4: CFB_CUDA_OK(d2h(p->subprobstartpts, nb + 1)); return 0;
         case 5: CFB_CUDA_OK(d2h(p->subprob_to_bin, (size_t)total)); return 0;
-        case 6: CFB_CUDA_OK(d2h(p->idxnupts, (size_t)(p->M > 0 ? p->M : 0))); return 0;
+        case 6:
+            if (int e = materialize_idxnupts(*p)) return e;
+            CFB_CUDA_OK(cudaStreamSynchronize(p->stream));
+            CFB_CUDA_OK(d2h(p->idxnupts, (size_t)(p->M > 0 ? p->M : 0)));
+            return 0;
         default: return CFB_ERR_BAD_ARG;
     }
 }

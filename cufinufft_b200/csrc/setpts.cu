@@ -1,5 +1,6 @@
-// setpts.cu -- the setpts hot path: bin histogram + in-bin rank, fused scans and
-// subproblem map, inverse permutation + bin-ordered rescaled coordinates.
+// setpts.cu -- the setpts hot path: one counting sort of the points by (bin, stencil cell),
+// bin counts / offsets and the subproblem map derived from it, and the bin-ordered point
+// records the spread / interp kernels stream.
 //
 // What the reference does (src/2d/spread2d_wrapper.cu:386-613, kernels
 // CalcBinSize_noghost_* / CalcInvertofGlobalSortIdx_* in src/{1,2,3}d/spreadinterp*.cu,
@@ -10,55 +11,183 @@
 //   idxnupts: a bin-major permutation (within-bin order is a race in the reference
 //   too, src/2d/spreadinterp2d.cu:120-121) --
 // with a different schedule, all stream-ordered with no host sync:
-//   K1 bin_count      warp-aggregated (match_any) histogram atomics -> rank per point
-//   K2 scan_bins      ONE kernel: exclusive scan of counts, integer ceil-div subproblem
-//                     counts, their inclusive scan and totalnumsubprob (device scalar)
-//   K3 map_subprob    one thread per subproblem slot, binary search in subprobstartpts
-//   K4 place_points   idxnupts + physically permuted, already-rescaled coordinates
-//                     (xs,ys,zs) so spread/interp read them coalesced and never
-//                     re-evaluate RESCALE (the reference recomputes it 3x per point).
-// Algorithmic bytes per point: K1 d*sF + 4, K4 d*sF + 4 + 4 + d*sF  (DESIGN.md).
+//   K1 key_count     key = bin * cells_per_bin + stencil cell inside the bin; warp-aggregated
+//                    (match_any) histogram atomics return the rank of each point in its key
+//   K2 scan_reduce / scan_top / scan_apply   three-phase exclusive scan of the key counts
+//   K3 bins_from_keys  binsize[b] = off[(b+1)*cpb] - off[b*cpb]
+//   K4 scan_bins     binstartpts, integer ceil-div subproblem counts, their inclusive scan and
+//                    totalnumsubprob (device scalar)
+//   K5 map_subprob   one thread per subproblem slot, binary search in subprobstartpts
+//   K6 place_points  ONE 16-byte (fp32) / 32-byte (fp64) record per point
+//                    {x_rescaled, y_rescaled, z_rescaled, original index} scattered to its sorted
+//                    slot: a single sector write per point instead of four, and the spread /
+//                    interp kernels read it back with one coalesced vector load and never
+//                    re-evaluate RESCALE (the reference recomputes it 3x per point per execute).
+// Sorting INSIDE the bin by stencil cell (the reference leaves that order to a race) makes
+// consecutive points share their whole stencil; the spread / interp kernels exploit that by
+// keeping a run of such points in registers (spreadinterp.cuh).  The fine histogram is used
+// when it is not much larger than the point set (nkeys <= 8 M + 2^22), otherwise the key is
+// the bin alone.
+// Algorithmic bytes per point: K1 d*sF + 4, K6 d*sF + 4 + 4 + rec  (DESIGN.md).
 #include "cfb_device.cuh"
 
 namespace cfb {
 
 template <typename T, int DIM>
-__device__ __forceinline__ int point_bin(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                                         int i, int nf1, int nf2, int nf3, int bs1, int bs2, int bs3,
-                                         int nb1, int nb2, int nb3, T &xr, T &yr, T &zr)
+__device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
+                                         int i, const SortGeo &g, T &xr, T &yr, T &zr)
 {
-    xr = rescale(x[i], nf1);
-    int b = bin_coord(xr, bs1, nb1);
-    if (DIM > 1) { yr = rescale(y[i], nf2); b += nb1 * bin_coord(yr, bs2, nb2); }
-    if (DIM > 2) { zr = rescale(z[i], nf3); b += nb1 * nb2 * bin_coord(zr, bs3, nb3); }
-    return b;
+    xr = rescale(x[i], g.nf[0]);
+    const int b1 = bin_coord(xr, g.bs[0], g.nb[0]);
+    int bin = b1, cell = 0;
+    if (g.nk[0] > 1) cell = stencil_cell(xr, g.ns, b1 * g.bs[0], g.nk[0]);
+    if (DIM > 1) {
+        yr = rescale(y[i], g.nf[1]);
+        const int b2 = bin_coord(yr, g.bs[1], g.nb[1]);
+        bin += g.nb[0] * b2;
+        if (g.nk[1] > 1) cell += g.nk[0] * stencil_cell(yr, g.ns, b2 * g.bs[1], g.nk[1]);
+    }
+    if (DIM > 2) {
+        zr = rescale(z[i], g.nf[2]);
+        const int b3 = bin_coord(zr, g.bs[2], g.nb[2]);
+        bin += g.nb[0] * g.nb[1] * b3;
+        if (g.nk[2] > 1) cell += g.nk[0] * g.nk[1] * stencil_cell(zr, g.ns, b3 * g.bs[2], g.nk[2]);
+    }
+    return bin * g.cpb + cell;
 }
 
-// K1: histogram + rank.  Lanes of a warp that fall in the same bin are aggregated into
-// one atomicAdd (clustered inputs put most of a warp in one bin).
+// K1: histogram + rank.  Lanes of a warp that fall on the same key are aggregated into
+// one atomicAdd (clustered inputs put most of a warp on one key).
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
-bin_count_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                 int nf1, int nf2, int nf3, int bs1, int bs2, int bs3, int nb1, int nb2, int nb3,
-                 int *__restrict__ binsize, int *__restrict__ sortidx)
+key_count_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
+                 const SortGeo g, int *__restrict__ keycnt, int *__restrict__ rank)
 {
     const int lane = threadIdx.x & 31;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
         int i = (int)(base + threadIdx.x);
         bool valid = i < M;
         T xr, yr, zr;
-        int b = valid ? point_bin<T, DIM>(x, y, z, i, nf1, nf2, nf3, bs1, bs2, bs3, nb1, nb2, nb3, xr, yr, zr) : -1 - lane;
-        unsigned peers = __match_any_sync(0xffffffffu, b);
+        int k = valid ? point_key<T, DIM>(x, y, z, i, g, xr, yr, zr) : -1 - lane;
+        unsigned peers = __match_any_sync(0xffffffffu, k);
         int leader = __ffs(peers) - 1;
         int rank_in_group = __popc(peers & ((1u << lane) - 1));
         int basecnt = 0;
-        if (valid && lane == leader) basecnt = atomicAdd(&binsize[b], __popc(peers));
+        if (valid && lane == leader) basecnt = atomicAdd(&keycnt[k], __popc(peers));
         basecnt = __shfl_sync(0xffffffffu, basecnt, leader);
-        if (valid) sortidx[i] = basecnt + rank_in_group;
+        if (valid) rank[i] = basecnt + rank_in_group;
     }
 }
 
-// K2: one block walks the bins in chunks of blockDim.x with a running carry.  Produces
+// ---- three-phase exclusive scan of n ints, in place, tiles of SCAN_TILE per block ----------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_PER_THREAD = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *wsum /*[32]*/, int &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    if (lane == 31) wsum[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < nw ? wsum[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    total = wsum[nw - 1];
+    int excl = s - v + (wid ? wsum[wid - 1] : 0);
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_reduce_kernel(long long n, const int *__restrict__ a, int *__restrict__ tilesum)
+{
+    __shared__ int wsum[32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_PER_THREAD;
+    int s = 0;
+    if (base + SCAN_PER_THREAD <= n) {
+        const int4 *p = reinterpret_cast<const int4 *>(a + base);
+#pragma unroll
+        for (int j = 0; j < SCAN_PER_THREAD / 4; ++j) { int4 v = p[j]; s += v.x + v.y + v.z + v.w; }
+    } else {
+        for (int j = 0; j < SCAN_PER_THREAD; ++j) if (base + j < n) s += a[base + j];
+    }
+    int total;
+    block_exclusive_scan(s, wsum, total);
+    if (threadIdx.x == 0) tilesum[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile sums (ntiles <= ~2^18 for 2^31 keys)
+__global__ void __launch_bounds__(1024)
+scan_top_kernel(int ntiles, int *__restrict__ tilesum)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < ntiles ? tilesum[i] : 0;
+        int total;
+        const int excl = block_exclusive_scan(v, wsum, total);
+        const int c = carry;
+        if (i < ntiles) tilesum[i] = c + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_kernel(long long n, int *__restrict__ a, const int *__restrict__ tilesum)
+{
+    __shared__ int wsum[32];
+    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_PER_THREAD;
+    int v[SCAN_PER_THREAD];
+    int s = 0;
+    const bool full = base + SCAN_PER_THREAD <= n;
+    if (full) {
+        const int4 *p = reinterpret_cast<const int4 *>(a + base);
+#pragma unroll
+        for (int j = 0; j < SCAN_PER_THREAD / 4; ++j) {
+            int4 q = p[j];
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_PER_THREAD; ++j) v[j] = base + j < n ? a[base + j] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; ++j) s += v[j];
+    int total;
+    int run = block_exclusive_scan(s, wsum, total) + tilesum[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; ++j) { const int t = v[j]; v[j] = run; run += t; }
+    if (full) {
+        int4 *p = reinterpret_cast<int4 *>(a + base);
+#pragma unroll
+        for (int j = 0; j < SCAN_PER_THREAD / 4; ++j) p[j] = make_int4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_PER_THREAD; ++j) if (base + j < n) a[base + j] = v[j];
+    }
+}
+
+// K3: bin counts from the key offsets (keyoff has nkeys+1 entries, keyoff[nkeys] = M)
+__global__ void __launch_bounds__(256)
+bins_from_keys_kernel(int nbins, int cpb, const int *__restrict__ keyoff, int *__restrict__ binsize)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbins) binsize[b] = keyoff[(size_t)(b + 1) * cpb] - keyoff[(size_t)b * cpb];
+}
+
+// K4: one block walks the bins in chunks of blockDim.x with a running carry.  Produces
 // binstartpts (exclusive), numsubprob = ceil(binsize/maxsub) (integer: the reference's float
 // ceil drops the last subproblem above 2^24 points per bin, precision_independent.cu:71),
 // subprobstartpts (inclusive scan with leading 0) and scalars[0] = totalnumsubprob.
@@ -107,7 +236,7 @@ scan_bins_kernel(int nbins, int maxsub, const int *__restrict__ binsize, int *__
     if (threadIdx.x == 0) scalars[0] = carry_b;
 }
 
-// K3: subprob_to_bin[s] = the bin whose slot range contains s (upper bound launch: slots
+// K5: subprob_to_bin[s] = the bin whose slot range contains s (upper bound launch: slots
 // beyond totalnumsubprob exit).  Replaces MapBintoSubProb_* + the blocking D2H/cudaMalloc.
 __global__ void __launch_bounds__(256)
 map_subprob_kernel(int nbins, int maxslots, const int *__restrict__ subprobstartpts,
@@ -123,23 +252,34 @@ map_subprob_kernel(int nbins, int maxslots, const int *__restrict__ subprobstart
     subprob_to_bin[s] = lo;
 }
 
-// K4: inverse permutation and bin-ordered rescaled coordinates.
+template <typename T>
+__device__ __forceinline__ void store_rec(PtRec<T> *dst, T xr, T yr, T zr, int i);
+template <>
+__device__ __forceinline__ void store_rec<float>(PtRec<float> *dst, float xr, float yr, float zr, int i)
+{
+    *reinterpret_cast<float4 *>(dst) = make_float4(xr, yr, zr, __int_as_float(i));
+}
+template <>
+__device__ __forceinline__ void store_rec<double>(PtRec<double> *dst, double xr, double yr, double zr, int i)
+{
+    double2 *d = reinterpret_cast<double2 *>(dst);
+    d[0] = make_double2(xr, yr);
+    d[1] = make_double2(zr, __longlong_as_double((long long)i));
+}
+
+// K6: scatter one record per point to its sorted slot.
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 place_points_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                    int nf1, int nf2, int nf3, int bs1, int bs2, int bs3, int nb1, int nb2, int nb3,
-                    const int *__restrict__ binstartpts, const int *__restrict__ sortidx,
-                    int *__restrict__ idxnupts, T *__restrict__ xs, T *__restrict__ ys, T *__restrict__ zs)
+                    const SortGeo g, const int *__restrict__ keyoff, const int *__restrict__ rank,
+                    PtRec<T> *__restrict__ recs)
 {
     for (long long ii = (long long)blockIdx.x * blockDim.x + threadIdx.x; ii < M; ii += (long long)gridDim.x * blockDim.x) {
         int i = (int)ii;
-        T xr, yr, zr;
-        int b = point_bin<T, DIM>(x, y, z, i, nf1, nf2, nf3, bs1, bs2, bs3, nb1, nb2, nb3, xr, yr, zr);
-        int pos = binstartpts[b] + sortidx[i];
-        idxnupts[pos] = i;
-        xs[pos] = xr;
-        if (DIM > 1) ys[pos] = yr;
-        if (DIM > 2) zs[pos] = zr;
+        T xr, yr = 0, zr = 0;
+        int k = point_key<T, DIM>(x, y, z, i, g, xr, yr, zr);
+        int pos = keyoff[k] + rank[i];
+        store_rec<T>(recs + pos, xr, yr, zr, i);
     }
 }
 
@@ -148,16 +288,23 @@ place_points_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, con
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 trivial_order_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                     int nf1, int nf2, int nf3, int *__restrict__ idxnupts, T *__restrict__ xs,
-                     T *__restrict__ ys, T *__restrict__ zs)
+                     int nf1, int nf2, int nf3, PtRec<T> *__restrict__ recs)
 {
     for (long long ii = (long long)blockIdx.x * blockDim.x + threadIdx.x; ii < M; ii += (long long)gridDim.x * blockDim.x) {
         int i = (int)ii;
-        idxnupts[i] = i;
-        xs[i] = rescale(x[i], nf1);
-        if (DIM > 1) ys[i] = rescale(y[i], nf2);
-        if (DIM > 2) zs[i] = rescale(z[i], nf3);
+        T xr = rescale(x[i], nf1), yr = 0, zr = 0;
+        if (DIM > 1) yr = rescale(y[i], nf2);
+        if (DIM > 2) zr = rescale(z[i], nf3);
+        store_rec<T>(recs + i, xr, yr, zr, i);
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+extract_idx_kernel(int M, const PtRec<T> *__restrict__ recs, int *__restrict__ idx)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x)
+        idx[i] = rec_index(recs[i]);
 }
 
 template <typename T, int DIM>
@@ -172,9 +319,10 @@ static int setpts_dim(Plan<T> &p)
     int *substart = p.subprobstartpts.template as<int>();
     int *s2b = p.subprob_to_bin.template as<int>();
     int *scal = p.scalars.template as<int>();
-    int *sortidx = p.sortidx.template as<int>();
-    int *idx = p.idxnupts.template as<int>();
-    T *xs = p.xs.template as<T>(), *ys = p.ys.template as<T>(), *zs = p.zs.template as<T>();
+    int *rank = p.sortidx.template as<int>();
+    int *keyoff = p.keyoff.template as<int>();
+    int *tilesum = p.tilesum.template as<int>();
+    PtRec<T> *recs = p.recs.template as<PtRec<T>>();
     const int threads = 256;
     long long want = ((long long)M + threads - 1) / threads;
     int blocks = (int)(want < 1 ? 1 : (want > (long long)p.num_sms * 32 ? (long long)p.num_sms * 32 : want));
@@ -182,27 +330,33 @@ static int setpts_dim(Plan<T> &p)
 
     if (!p.sorted) {
         if (M > 0) {
-            trivial_order_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, p.nf1, p.nf2, p.nf3, idx, xs, ys, zs);
+            trivial_order_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, p.nf1, p.nf2, p.nf3, recs);
             p.launches_setpts++;
         }
         CFB_CUDA_OK(cudaMemsetAsync(scal, 0, 8 * sizeof(int), st));
         CFB_CUDA_OK(cudaGetLastError());
         return 0;
     }
-    CFB_CUDA_OK(cudaMemsetAsync(binsize, 0, sizeof(int) * (size_t)p.nbins, st));
+    const SortGeo g = p.sortgeo;
+    const long long nkeys = (long long)p.nbins * g.cpb;
+    const long long nscan = nkeys + 1;                       // trailing total
+    const int ntiles = (int)((nscan + SCAN_TILE - 1) / SCAN_TILE);
+    CFB_CUDA_OK(cudaMemsetAsync(keyoff, 0, sizeof(int) * (size_t)nscan, st));
     if (M > 0) {
-        bin_count_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, p.nf1, p.nf2, p.nf3, p.bs[0], p.bs[1], p.bs[2],
-                                                           p.nbin[0], p.nbin[1], p.nbin[2], binsize, sortidx);
+        key_count_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, g, keyoff, rank);
         p.launches_setpts++;
     }
+    scan_reduce_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nscan, keyoff, tilesum);
+    scan_top_kernel<<<1, 1024, 0, st>>>(ntiles, tilesum);
+    scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nscan, keyoff, tilesum);
+    bins_from_keys_kernel<<<(p.nbins + 255) / 256, 256, 0, st>>>(p.nbins, g.cpb, keyoff, binsize);
     scan_bins_kernel<<<1, 1024, 0, st>>>(p.nbins, p.opts.gpu_maxsubprobsize, binsize, binstart, nsub, substart, scal);
-    p.launches_setpts++;
+    p.launches_setpts += 5;
     int maxslots = p.nbins + M / p.opts.gpu_maxsubprobsize + 1;
     map_subprob_kernel<<<(maxslots + 255) / 256, 256, 0, st>>>(p.nbins, maxslots, substart, scal, s2b);
     p.launches_setpts++;
     if (M > 0) {
-        place_points_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, p.nf1, p.nf2, p.nf3, p.bs[0], p.bs[1], p.bs[2],
-                                                              p.nbin[0], p.nbin[1], p.nbin[2], binstart, sortidx, idx, xs, ys, zs);
+        place_points_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, g, keyoff, rank, recs);
         p.launches_setpts++;
     }
     CFB_CUDA_OK(cudaGetLastError());
@@ -213,20 +367,55 @@ template <typename T>
 int stage_setpts(Plan<T> &p)
 {
     const size_t M = (size_t)(p.M > 0 ? p.M : 1);
-    CFB_CUDA_OK(p.sortidx.reserve(M * sizeof(int)));
-    CFB_CUDA_OK(p.idxnupts.reserve(M * sizeof(int)));
-    CFB_CUDA_OK(p.xs.reserve(M * sizeof(T)));
-    if (p.dim > 1) CFB_CUDA_OK(p.ys.reserve(M * sizeof(T)));
-    if (p.dim > 2) CFB_CUDA_OK(p.zs.reserve(M * sizeof(T)));
+    // key space: (bin, stencil cell in bin) when that histogram is not much larger than the
+    // point set, else the bin alone
+    SortGeo &g = p.sortgeo;
+    const int nf[3] = {p.nf1, p.nf2, p.nf3};
+    g.ns = p.ns;
+    long long cpb = 1;
+    for (int d = 0; d < 3; ++d) {
+        g.nf[d] = nf[d]; g.bs[d] = p.bs[d]; g.nb[d] = p.nbin[d];
+        g.nk[d] = d < p.dim ? p.bs[d] + (p.ns & 1) : 1;
+        cpb *= g.nk[d];
+    }
+    long long nkeys = cpb * p.nbins;
+    if (!p.fine_sort_allowed || nkeys > 8LL * (long long)M + (1LL << 22) || nkeys > 2000000000LL) {
+        g.nk[0] = g.nk[1] = g.nk[2] = 1;
+        cpb = 1;
+        nkeys = p.nbins;
+    }
+    g.cpb = (int)cpb;
+    CFB_CUDA_OK(p.recs.reserve(M * sizeof(PtRec<T>)));
+    if (p.sorted) {
+        CFB_CUDA_OK(p.sortidx.reserve(M * sizeof(int)));
+        CFB_CUDA_OK(p.keyoff.reserve(((size_t)nkeys + 1 + 4) * sizeof(int)));
+        CFB_CUDA_OK(p.tilesum.reserve(((size_t)(nkeys + 1) / SCAN_TILE + 2) * sizeof(int)));
+    }
     size_t maxslots = (size_t)p.nbins + M / (size_t)p.opts.gpu_maxsubprobsize + 1;
     CFB_CUDA_OK(p.subprob_to_bin.reserve(maxslots * sizeof(int)));
+    p.idx_valid = false;
     switch (p.dim) {
         case 1: return setpts_dim<T, 1>(p);
         case 2: return setpts_dim<T, 2>(p);
         default: return setpts_dim<T, 3>(p);
     }
 }
+
+// idxnupts is materialised only when somebody asks for it (plan introspection)
+template <typename T>
+int materialize_idxnupts(Plan<T> &p)
+{
+    if (p.idx_valid || p.M <= 0) return 0;
+    CFB_CUDA_OK(p.idxnupts.reserve((size_t)p.M * sizeof(int)));
+    extract_idx_kernel<T><<<p.num_sms * 8, 256, 0, p.stream>>>(p.M, p.recs.template as<PtRec<T>>(), p.idxnupts.template as<int>());
+    CFB_CUDA_OK(cudaGetLastError());
+    p.idx_valid = true;
+    return 0;
+}
+
 template int stage_setpts<float>(Plan<float> &);
 template int stage_setpts<double>(Plan<double> &);
+template int materialize_idxnupts<float>(Plan<float> &);
+template int materialize_idxnupts<double>(Plan<double> &);
 
 }  // namespace cfb

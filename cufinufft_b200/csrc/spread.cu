@@ -90,9 +90,9 @@ void plan_tile_geometry(Plan<T> &p)
     }
     size_t avail = (size_t)p.max_smem_optin - 18 * 16 * sizeof(T) - 1024;
     long long w = cells > (1 << 24) ? 0 : (long long)(avail / per_warp);
-    if (w > 16) {                       // several blocks per SM instead of one huge block
-        w = 8;
-    }
+    const int maxw = sm_spread_max_warps(p.dim, p.ns, (int)sizeof(T));
+    if (w > 16) w = 8;                  // several blocks per SM instead of one huge block
+    if (w > maxw) w = maxw;
     p.sm_warps = (int)w;
 }
 

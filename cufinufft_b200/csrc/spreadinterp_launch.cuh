@@ -15,8 +15,7 @@ template <typename T>
 static SIArgs<T> make_args(Plan<T> &p, int nt)
 {
     SIArgs<T> a;
-    a.xs = p.xs.template as<T>(); a.ys = p.ys.template as<T>(); a.zs = p.zs.template as<T>();
-    a.idx = p.idxnupts.template as<int>();
+    a.recs = p.recs.template as<PtRec<T>>();
     a.c = nullptr; a.fw = nullptr;
     a.binstart = p.binstartpts.template as<int>(); a.binsize = p.binsize.template as<int>();
     a.s2b = p.subprob_to_bin.template as<int>(); a.substart = p.subprobstartpts.template as<int>();
@@ -51,9 +50,9 @@ static int do_spread(Plan<T> &p, SIArgs<T> &a)
         spread_sm_kernel<T, DIM, NS><<<p.num_sms * blocks_per_sm, 32 * p.sm_warps, smem, p.stream>>>(a);
     } else {
         const int warps = 8;
-        size_t smem = head + warps * (warp_scratch_bytes<T, DIM, NS>() + 2 * 32 * sizeof(int));
+        size_t smem = head + warps * warp_scratch_bytes<T, DIM, NS>();
         CFB_CUDA_OK(cudaFuncSetAttribute(spread_gm_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        long long nb = (((long long)p.M + 31) / 32 * a.nt + warps - 1) / warps;
+        long long nb = (((long long)p.M + 255) / 256 * a.nt + warps - 1) / warps;
         long long cap = (long long)p.num_sms * 8;
         int blocks = (int)(nb < 1 ? 1 : (nb > cap ? cap : nb));
         spread_gm_kernel<T, DIM, NS><<<blocks, 32 * warps, smem, p.stream>>>(a);
@@ -68,9 +67,9 @@ static int do_interp(Plan<T> &p, SIArgs<T> &a)
 {
     const size_t head = 18 * 16 * sizeof(T);
     const int warps = 8;
-    size_t smem = head + warps * (warp_scratch_bytes<T, DIM, NS>() + 2 * 32 * sizeof(int));
+    size_t smem = head + warps * warp_scratch_bytes<T, DIM, NS>();
     CFB_CUDA_OK(cudaFuncSetAttribute(interp_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long nb = (((long long)p.M + 31) / 32 * a.nt + warps - 1) / warps;
+    long long nb = (((long long)p.M + 255) / 256 * a.nt + warps - 1) / warps;
     long long cap = (long long)p.num_sms * 8;
     int blocks = (int)(nb < 1 ? 1 : (nb > cap ? cap : nb));
     interp_kernel<T, DIM, NS><<<blocks, 32 * warps, smem, p.stream>>>(a);
