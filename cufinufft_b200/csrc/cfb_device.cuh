@@ -64,42 +64,109 @@ __device__ __forceinline__ PtRec<double> load_rec(const PtRec<double> *p)
 }
 
 // ---- exp(beta*sqrt(1 - c x^2)) for |x| < ns/2, un-normalised as in the reference
-// (src/cuspreadinterp.h:6-16).  fp64 plans evaluate in double (bit-compatible formula);
-// fp32 plans evaluate in fp32 (the reference promotes to double here; our deviation is
-// <= ~1e-6 relative, budgeted inside the 1e-5 parity tolerance).
+// (src/cuspreadinterp.h:6-16, which evaluates sqrt and exp in double even in the fp32 build).
+// Both versions are straight-line code without the special-case branches of libdevice:
+//   sqrt(t), t in [0,1]: MUFU rsqrt seed + Newton steps;  exp(y), y in [0, 40]: y = n ln2 + r,
+//   2^n applied to the exponent field.
+// fp32: argument reduction in two-term precision + ex2.approx: relative error ~1e-7 per weight
+//       (the reference's own double->float rounding is 6e-8).   fp64: degree-13 polynomial, ~1 ulp.
 __device__ __forceinline__ float es_eval(float ax, float es_c, float es_beta, float half)
 {
-    float t = fmaf(-es_c * ax, ax, 1.0f);
-    float v = expf(es_beta * sqrtf(fmaxf(t, 0.0f)));
-    return ax < half ? v : 0.0f;
+    const float t = fmaf(-es_c * ax, ax, 1.0f);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    float s = t * r;
+    const float e = fmaf(-s, s, t);
+    s = fmaf(e * 0.5f, r, s);
+    s = t > 0.0f ? s : 0.0f;                 // support edge: rsqrt(0) = inf
+    const float y = es_beta * s;
+    const float L = 1.4426950216293335f, Llo = 1.9259629911266175e-08f;     // log2(e) = L + Llo
+    const float n = rintf(y * L);
+    float f = fmaf(y, L, -n);
+    f = fmaf(y, Llo, f);
+    float p, q;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(n));                   // exact power of two
+    return ax < half ? p * q : 0.0f;
 }
 __device__ __forceinline__ double es_eval(double ax, double es_c, double es_beta, double half)
 {
-    double t = 1.0 - es_c * ax * ax;
-    double v = exp(es_beta * sqrt(fmax(t, 0.0)));
-    return ax < half ? v : 0.0;
+    const double t = 1.0 - es_c * ax * ax;
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));
+    double s = t * r;
+    const double h = 0.5 * r;
+    double e = fma(-s, s, t);
+    s = fma(e, h, s);
+    e = fma(-s, s, t);
+    s = fma(e, h, s);
+    e = fma(-s, s, t);
+    s = fma(e, h, s);
+    s = t > 0.0 ? s : 0.0;
+    const double y = es_beta * s;
+    const double magic = 6755399441055744.0;                                // 1.5 * 2^52
+    const double z = fma(y, 1.4426950408889634, magic);
+    const int n = __double2loint(z);
+    const double nd = z - magic;
+    double q = fma(-nd, 6.93147180369123816490e-01, y);                     // ln2 high 32 bits (exact product)
+    q = fma(-nd, 1.90821492927058770002e-10, q);
+    double p = 1.6059043836821613e-10;                                      // 1/13!
+    p = fma(p, q, 2.08767569878681e-09);
+    p = fma(p, q, 2.505210838544172e-08);
+    p = fma(p, q, 2.755731922398589e-07);
+    p = fma(p, q, 2.7557319223985893e-06);
+    p = fma(p, q, 2.48015873015873e-05);
+    p = fma(p, q, 1.984126984126984e-04);
+    p = fma(p, q, 1.388888888888889e-03);
+    p = fma(p, q, 8.333333333333333e-03);
+    p = fma(p, q, 4.1666666666666664e-02);
+    p = fma(p, q, 1.6666666666666666e-01);
+    p = fma(p, q, 0.5);
+    p = fma(p, q, 1.0);
+    p = fma(p, q, 1.0);
+    p = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return ax < half ? p : 0.0;
 }
 
-// Kernel vector of one coordinate: ker[i] = phi(|x1 + i|), i < NS  (eval_kernel_vec,
-// src/cuspreadinterp.h:33-40) or the Horner piecewise polynomial (:18-31) with
-// coefficients hc[k*NS + i] (T, staged in shared memory by the caller).
-template <typename T, int NS>
-__device__ __forceinline__ void kernel_vector(T *ker, T x1, T es_c, T es_beta, bool horner, const T *hc, int ncoef)
+// Kernel values of one coordinate: dst[slot] = phi(|x1 + i|) for the NS stencil points
+// (eval_kernel_vec, src/cuspreadinterp.h:33-40) or the Horner piecewise polynomial (:18-31) with
+// coefficients hc[k*NS + i] (T, staged in shared memory by the caller).  `dst` may be a register
+// array (UNROLL) or shared memory.
+template <typename T, int NS, bool UNROLL>
+__device__ __forceinline__ void kernel_vector(T *dst, T x1, T es_c, T es_beta, bool horner, const T *hc, int ncoef)
 {
     if (!horner) {
+        if (UNROLL) {
 #pragma unroll
-        for (int i = 0; i < NS; ++i) {
-            T a = x1 + (T)i;
-            a = a < 0 ? -a : a;
-            ker[i] = es_eval(a, es_c, es_beta, (T)(NS * 0.5));
+            for (int i = 0; i < NS; ++i) {
+                T a = x1 + (T)i;
+                a = a < 0 ? -a : a;
+                dst[i] = es_eval(a, es_c, es_beta, (T)(NS * 0.5));
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < NS; ++i) {
+                T a = x1 + (T)i;
+                a = a < 0 ? -a : a;
+                dst[i] = es_eval(a, es_c, es_beta, (T)(NS * 0.5));
+            }
         }
     } else {
-        T z = (T)(2 * (double)x1 + NS - 1.0);
+        const T z = (T)(2 * (double)x1 + NS - 1.0);
+        if (UNROLL) {
 #pragma unroll
-        for (int i = 0; i < NS; ++i) ker[i] = hc[(ncoef - 1) * NS + i];
-        for (int k = ncoef - 2; k >= 0; --k) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) ker[i] = fma(z, ker[i], hc[k * NS + i]);
+            for (int i = 0; i < NS; ++i) {
+                T acc = hc[(ncoef - 1) * NS + i];
+                for (int k = ncoef - 2; k >= 0; --k) acc = fma(z, acc, hc[k * NS + i]);
+                dst[i] = acc;
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < NS; ++i) {
+                T acc = hc[(ncoef - 1) * NS + i];
+                for (int k = ncoef - 2; k >= 0; --k) acc = fma(z, acc, hc[k * NS + i]);
+                dst[i] = acc;
+            }
         }
     }
 }

@@ -9,20 +9,21 @@
 // Design (DESIGN.md "spread" / "interp").  The reference gives every point to one thread that
 // does 2*ns^d scalar atomics (shared or global).  Here
 //  * a WARP owns a batch of 32 consecutive sorted points.  Phase A is thread-per-point: one
-//    16/32-byte record load, the d*ns kernel values (exp/sqrt or Horner), the strength gather,
-//    all parked in a small per-warp scratch.  Phase B is lane-per-cell: the 32 lanes are laid
-//    over the point's stencil, lane = (row r, column ix), ITERS passes cover all rows.
+//    16/32-byte record (prefetched two batches ahead), the d*ns kernel values (exp/sqrt or
+//    Horner), the strength gather (prefetched one batch ahead), all parked in a small per-warp
+//    scratch.  Phase B is lane-per-cell: the 32 lanes are laid over the point's stencil,
+//    lane = (row r, column ix), ITERS passes cover all rows.
 //  * setpts sorts points by (bin, stencil origin), so consecutive points usually share their
 //    WHOLE stencil.  Such a RUN is accumulated in registers (ITERS complex accumulators per
-//    lane) and touches memory once per run instead of once per point:
+//    lane, packed f32x2 FMAs in fp32) and touches memory once per run instead of once per point:
 //      spread SM : run -> warp-private padded bin tile in shared memory with plain LDS/FADD/STS
 //                  (lanes of one flush hit distinct cells, padded strides keep them on distinct
 //                  banks: no shared atomics at all); tile -> fine grid once per subproblem with
-//                  vector RED (red.global.add.v2.f32), zero cells skipped
+//                  vector RED (red.global.add.v2.f32) over the touched rows only, cleared on the way
 //      spread GM : run -> fine grid directly with vector RED
 //      interp    : the stencil's grid values are loaded once per run (coalesced row segments)
-//                  and reused from registers for every point of the run; per-point partial sums
-//                  of 8 points are reduced together by one transposing shuffle butterfly
+//                  and reused from registers for every point of the run; the 32 per-lane partial
+//                  sums of 8 points are transposed through shared memory and reduced together
 //    With one point per run this degenerates to the per-point version; clustered inputs (the
 //    reference's worst case: atomic contention) become the best case.
 //  * Subproblems (the reference's (bin, <= maxsubprobsize points) units, same subprob_to_bin
@@ -53,16 +54,30 @@ struct SIArgs {
     long long fwstride;
 };
 
+constexpr int roundup(int v, int m) { return (v + m - 1) / m * m; }
+
+// Stencil geometry of one (precision, dimension, width) instantiation.
+// Scratch row of a point (T units), VEC layout: [kx: NSX][W: R x WS] with W[r][it] the row weight
+// of pass `it` for lanes of row-slot r (2-D: ky[it*R+r]; 3-D: ky[iy]*kz[iz], row = it*R+r =
+// iz*NS+iy; zero beyond ROWS), every segment 16-byte aligned so phase B reads it with LDS.128.
+// SCALAR layout (3-D without precomputed products): [kx: NS][ky: NS][kz: NS].
 template <typename T, int DIM, int NS> struct Geo {
-    static constexpr int R = 32 / NS;                                    // stencil rows per warp pass
-    static constexpr int LANES = R * NS;                                 // active lanes
+    static constexpr int V = 16 / (int)sizeof(T);                         // reals per 16-byte vector
+    static constexpr int R = 32 / NS;                                     // stencil rows per warp pass
+    static constexpr int LANES = R * NS;                                  // active lanes
     static constexpr int ROWS = DIM == 1 ? 1 : (DIM == 2 ? NS : NS * NS);
     static constexpr int ITERS = (ROWS + R - 1) / R;
-    static constexpr bool PROD = DIM == 3 && NS <= 7;                    // ky*kz products precomputed per point
-    static constexpr int NW = DIM == 1 ? 0 : ((DIM == 2 || PROD) ? ITERS * R : 2 * NS);   // row weights (zero padded)
-    static constexpr int KP = (NS + NW) | 1;                             // odd stride: conflict-free scratch
-    static constexpr bool MERGE = ITERS * (int)(sizeof(T) / 4) <= 72;    // run accumulators fit in registers
-    static constexpr bool TOFF_REGS = sizeof(T) == 4 || ITERS <= 16;     // per-pass tile offsets kept in registers
+    static constexpr bool PROD = DIM == 3 && NS <= 7 && sizeof(T) == 4;   // ky*kz products precomputed per point
+    static constexpr bool VEC = DIM == 2 || PROD;
+    static constexpr int NSX = VEC ? roundup(NS, V) : NS;
+    static constexpr int WS = roundup(ITERS, V);
+    static constexpr int KP0 = DIM == 1 ? NS : (VEC ? NSX + R * WS : 3 * NS);
+    // VEC: KP/V odd (vector phase-A stores and phase-B loads conflict-free); else KP odd
+    static constexpr int KP = VEC ? (((KP0 / V) | 1) * V) : (KP0 | 1);
+    static constexpr int NACC = VEC ? WS : (DIM == 1 ? 1 : roundup(ITERS, 2));   // accumulator slots (padded passes have weight 0)
+    static constexpr bool PREFETCH = NACC * (int)(sizeof(T) / 4) <= 16;  // next point's weights fetched one point ahead
+    static constexpr bool MERGE = NACC * (int)(sizeof(T) / 4) <= 72;      // run accumulators fit in registers
+    static constexpr bool TOFF_REGS = sizeof(T) == 4 || ITERS <= 16;      // per-pass tile offsets kept in registers
     static constexpr int SM_MAXW = ITERS * (int)(sizeof(T) / 4) > 24 ? 4 : 16;   // warps per SM-spread block (register budget)
 };
 
@@ -73,79 +88,175 @@ inline int sm_spread_max_warps(int dim, int ns, int real_bytes)
     return iters * (real_bytes / 4) > 24 ? 4 : 16;
 }
 
-// bytes of per-warp scratch: ker[32*KP] T | c[32] C | x0,y0,z0[32] int
+// bytes of per-warp scratch: ker[32*KP] T | c[32] C | x0,y0,z0[32] int | red[8*33] C (interp only uses it)
 template <typename T, int DIM, int NS>
 __host__ __device__ constexpr size_t warp_scratch_bytes()
 {
-    return (size_t)32 * Geo<T, DIM, NS>::KP * sizeof(T) + 32 * 2 * sizeof(T) + 3 * 32 * sizeof(int);
+    return (size_t)32 * Geo<T, DIM, NS>::KP * sizeof(T) + 32 * 2 * sizeof(T) + 3 * 32 * sizeof(int) + 8 * 34 * 2 * sizeof(T);
 }
 
 template <typename T, int DIM, int NS>
 struct Scratch {
-    T *ker; typename cplx_of<T>::type *c; int *x0, *y0, *z0;
+    using C = typename cplx_of<T>::type;
+    T *ker; C *c; int *x0, *y0, *z0; C *red;
     __device__ __forceinline__ explicit Scratch(unsigned char *base)
     {
         using G = Geo<T, DIM, NS>;
         ker = reinterpret_cast<T *>(base);
-        c = reinterpret_cast<typename cplx_of<T>::type *>(ker + 32 * G::KP);
+        c = reinterpret_cast<C *>(ker + 32 * G::KP);
         x0 = reinterpret_cast<int *>(c + 32);
         y0 = x0 + 32;
         z0 = y0 + 32;
+        red = reinterpret_cast<C *>(z0 + 32);
     }
 };
 
+template <typename T> struct vec16;
+template <> struct vec16<float>  { using type = float4; };
+template <> struct vec16<double> { using type = double2; };
+
 // ---- phase A: thread-per-point kernel weights into the per-warp scratch ------
-// ker row of the point: [0,NS) x weights; then row weights: 2-D ky[NS] (zero padded to ITERS*R);
-// 3-D PROD ky[iy]*kz[iz] at iz*NS+iy (zero padded); 3-D !PROD ky[NS], kz[NS].
 template <typename T, int DIM, int NS>
 __device__ __forceinline__ void point_weights(const SIArgs<T> &a, const PtRec<T> &rec, T *kp, const T *s_hc,
                                               int &xstart, int &ystart, int &zstart)
 {
     using G = Geo<T, DIM, NS>;
-    T ker[NS];
+    constexpr bool F32 = sizeof(T) == 4;
     xstart = stencil_start(rec.x, NS);
-    kernel_vector<T, NS>(ker, (T)xstart - rec.x, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+    if (DIM > 1) ystart = stencil_start(rec.y, NS);
+    if (DIM > 2) zstart = stencil_start(rec.z, NS);
+    const T x1 = (T)xstart - rec.x;
+    if constexpr (!G::VEC) {
+        // 1-D, or 3-D with on-the-fly products: plain [kx][ky][kz]
+        kernel_vector<T, NS, F32>(kp, x1, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+        if (DIM == 3) {
+            kernel_vector<T, NS, F32>(kp + NS, (T)ystart - rec.y, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+            kernel_vector<T, NS, F32>(kp + 2 * NS, (T)zstart - rec.z, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+        }
+    } else if constexpr (F32) {
+        // everything in registers, written with 16-byte stores
+        float kx[G::NSX], ky[NS], kz[NS];
+        kernel_vector<T, NS, true>(kx, x1, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) kp[i] = ker[i];
-    if (DIM == 2) {
-        ystart = stencil_start(rec.y, NS);
-        kernel_vector<T, NS>(ker, (T)ystart - rec.y, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+        for (int i = NS; i < G::NSX; ++i) kx[i] = 0;
+        kernel_vector<T, NS, true>(ky, (T)ystart - rec.y, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+        if (DIM == 3) kernel_vector<T, NS, true>(kz, (T)zstart - rec.z, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+        float4 *dst = reinterpret_cast<float4 *>(kp);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) kp[NS + i] = ker[i];
+        for (int i = 0; i < G::NSX / 4; ++i) dst[i] = make_float4(kx[4 * i], kx[4 * i + 1], kx[4 * i + 2], kx[4 * i + 3]);
+        auto wgt = [&](int r, int it) -> float {
+            const int row = it * G::R + r;
+            if (it >= G::ITERS || row >= G::ROWS) return 0.0f;
+            if (DIM == 2) return ky[row];
+            return ky[row % NS] * kz[row / NS];
+        };
 #pragma unroll
-        for (int i = NS; i < G::NW; ++i) kp[NS + i] = 0;
-    }
-    if (DIM == 3) {
-        T kz[NS];
-        ystart = stencil_start(rec.y, NS);
-        kernel_vector<T, NS>(ker, (T)ystart - rec.y, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
-        zstart = stencil_start(rec.z, NS);
-        kernel_vector<T, NS>(kz, (T)zstart - rec.z, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
-        if (G::PROD) {
+        for (int r = 0; r < G::R; ++r)
 #pragma unroll
-            for (int iz = 0; iz < NS; ++iz)
+            for (int it = 0; it < G::WS; it += 4)
+                dst[(G::NSX + r * G::WS + it) / 4] = make_float4(wgt(r, it), wgt(r, it + 1), wgt(r, it + 2), wgt(r, it + 3));
+    } else {
+        // fp64 2-D: evaluate straight into the slots (no unrolling: the evaluation is long)
+        kernel_vector<T, NS, false>(kp, x1, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
 #pragma unroll
-                for (int iy = 0; iy < NS; ++iy) kp[NS + iz * NS + iy] = ker[iy] * kz[iz];
-#pragma unroll
-            for (int i = NS * NS; i < G::NW; ++i) kp[NS + i] = 0;
+        for (int i = NS; i < G::NSX; ++i) kp[i] = 0;
+        const T y1 = (T)ystart - rec.y;
+        if (!a.horner) {
+#pragma unroll 1
+            for (int slot = 0; slot < G::R * G::WS; ++slot) {
+                const int r = slot / G::WS, it = slot - r * G::WS, row = it * G::R + r;
+                T v = 0;
+                if (it < G::ITERS && row < G::ROWS) {
+                    T ax = y1 + (T)row;
+                    ax = ax < 0 ? -ax : ax;
+                    v = es_eval(ax, a.es_c, a.es_beta, (T)(NS * 0.5));
+                }
+                kp[G::NSX + slot] = v;
+            }
         } else {
+            T ky[NS];
+            kernel_vector<T, NS, true>(ky, y1, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) { kp[NS + i] = ker[i]; kp[2 * NS + i] = kz[i]; }
+            for (int r = 0; r < G::R; ++r)
+#pragma unroll
+                for (int it = 0; it < G::WS; ++it) {
+                    const int row = it * G::R + r;
+                    kp[G::NSX + r * G::WS + it] = (it < G::ITERS && row < G::ROWS) ? ky[row] : (T)0;
+                }
         }
     }
 }
 
-// row weight of pass `it` for this lane (row = it*R + r)
+// row weights of all passes for this lane (row-slot r) into w[NACC]
 template <typename T, int DIM, int NS>
-__device__ __forceinline__ T row_weight(const T *kq, int it, int r)
+__device__ __forceinline__ void load_row_weights(const T *kq, int r, T (&w)[Geo<T, DIM, NS>::NACC])
 {
     using G = Geo<T, DIM, NS>;
-    if (DIM == 1) return (T)1;
-    const int row = it * G::R + r;
-    if (DIM == 2 || G::PROD) return kq[NS + row];
-    const int iz = row / NS, iy = row - iz * NS;
-    return row < G::ROWS ? kq[NS + iy] * kq[2 * NS + iz] : (T)0;
+    if constexpr (DIM == 1) {
+        w[0] = (T)1;
+    } else if constexpr (G::VEC) {
+        using V16 = typename vec16<T>::type;
+        const V16 *src = reinterpret_cast<const V16 *>(kq + G::NSX + r * G::WS);
+#pragma unroll
+        for (int j = 0; j < G::WS / G::V; ++j) {
+            const V16 v = src[j];
+            if constexpr (sizeof(T) == 4) { w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w; }
+            else { w[2 * j] = v.x; w[2 * j + 1] = v.y; }
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < G::NACC; ++it) {
+            const int row = it * G::R + r;
+            const int iz = row / NS, iy = row - iz * NS;
+            w[it] = (it < G::ITERS && row < G::ROWS) ? kq[NS + iy] * kq[2 * NS + iz] : (T)0;
+        }
+    }
 }
+
+// acc[it] += (cr, ci) * w[it] for all passes.  fp32: packed f32x2 FMAs over PAIRS OF PASSES
+// (accumulators are stored as (x_it, x_it+1), (y_it, y_it+1)); fp64: scalar DFMA.
+template <typename T, int N> struct RunAcc;
+template <int N> struct RunAcc<float, N> {
+    static_assert(N % 2 == 0 || N == 1, "padded pass count");
+    static constexpr int NP = (N + 1) / 2;
+    unsigned long long ax[NP], ay[NP];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { ax[j] = 0ull; ay[j] = 0ull; }
+    }
+    __device__ __forceinline__ static unsigned long long pack(float lo, float hi) {
+        unsigned long long v;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+        return v;
+    }
+    __device__ __forceinline__ void fma(float cr, float ci, const float (&w)[N]) {
+        const unsigned long long cr2 = pack(cr, cr), ci2 = pack(ci, ci);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const unsigned long long w2 = pack(w[2 * j], N > 1 ? w[2 * j + (N > 1 ? 1 : 0)] : 0.0f);
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ax[j]) : "l"(cr2), "l"(w2));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ay[j]) : "l"(ci2), "l"(w2));
+        }
+    }
+    __device__ __forceinline__ float2 get(int it) const {
+        float xl, xh, yl, yh;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(xl), "=f"(xh) : "l"(ax[it >> 1]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(yl), "=f"(yh) : "l"(ay[it >> 1]));
+        return (it & 1) ? make_float2(xh, yh) : make_float2(xl, yl);
+    }
+};
+template <int N> struct RunAcc<double, N> {
+    double ax[N], ay[N];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int j = 0; j < N; ++j) { ax[j] = 0; ay[j] = 0; }
+    }
+    __device__ __forceinline__ void fma(double cr, double ci, const double (&w)[N]) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) { ax[j] = ::fma(cr, w[j], ax[j]); ay[j] = ::fma(ci, w[j], ay[j]); }
+    }
+    __device__ __forceinline__ double2 get(int it) const { return make_double2(ax[it], ay[it]); }
+};
 
 template <typename T, int NS>
 __device__ __forceinline__ const T *stage_horner(const SIArgs<T> &a, T *s_hc)
@@ -157,6 +268,9 @@ __device__ __forceinline__ const T *stage_horner(const SIArgs<T> &a, T *s_hc)
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+template <typename T>
+__device__ __forceinline__ PtRec<T> null_rec() { PtRec<T> r; r.x = 0; r.y = 0; r.z = 0; r.idx = 0; return r; }
 
 // =============================================================================
 // SM spread: warp-private tile, run accumulation in registers, lane-per-cell flushes.
@@ -202,6 +316,9 @@ spread_sm_kernel(const SIArgs<T> a)
         return iz * a.sz + iy * a.sy;
     };
 
+    // the tile is clean whenever a work item starts: cleared here once, then by every flush
+    for (int i = lane; i < a.tile_cells; i += 32) { tile[i].x = 0; tile[i].y = 0; }
+
     for (;;) {
         long long w = 0;
         if (lane == 0) w = atomicAdd(a.counter, 1);
@@ -217,15 +334,12 @@ spread_sm_kernel(const SIArgs<T> a)
         const int ox = b1 * a.bs1 - a.pad, oy = b2 * a.bs2 - a.pad, oz = b3 * a.bs3 - a.pad;
         const C *cin = a.c + (size_t)t * a.M;
         C *fwt = a.fw + (size_t)t * a.fwstride;
+        const PtRec<T> *recs = a.recs + pstart;
 
-        for (int i = lane; i < a.tile_cells; i += 32) { tile[i].x = 0; tile[i].y = 0; }
-
-        C acc[G::MERGE ? G::ITERS : 1];
-        if (G::MERGE) {
-#pragma unroll
-            for (int it = 0; it < G::ITERS; ++it) { acc[it].x = 0; acc[it].y = 0; }
-        }
+        RunAcc<T, G::MERGE ? G::NACC : 1> acc;
+        acc.zero();
         int cur = -1;                                   // tile offset of the open run
+        int ylo = 1 << 30, yhi = -1, zlo = 1 << 30, zhi = -1;   // touched stencil origins (tile rows), per lane
 
         // add the open run's accumulators into the tile (lanes touch distinct cells)
         auto flush_run = [&]() {
@@ -237,26 +351,33 @@ spread_sm_kernel(const SIArgs<T> a)
                     if (active && it * G::R + r < G::ROWS) {
                         C *cell = cell0 + tile_off(it);
                         C v = *cell;
-                        v.x += acc[it].x; v.y += acc[it].y;
+                        const C d = acc.get(it);
+                        v.x += d.x; v.y += d.y;
                         *cell = v;
                     }
-                    acc[it].x = 0; acc[it].y = 0;
                 }
+                acc.zero();
             }
         };
 
+        // software pipeline: records two batches ahead, strengths one batch ahead
+        PtRec<T> rec_cur = lane < n ? load_rec(recs + lane) : null_rec<T>();
+        PtRec<T> rec_nxt = 32 + lane < n ? load_rec(recs + 32 + lane) : null_rec<T>();
+        C c_cur = lane < n ? cin[rec_index(rec_cur)] : C{0, 0};
+
         for (int base = 0; base < n; base += 32) {
             const int cnt = min(32, n - base);
+            C c_nxt = base + 32 + lane < n ? cin[rec_index(rec_nxt)] : C{0, 0};
+            PtRec<T> rec_nn = base + 64 + lane < n ? load_rec(recs + base + 64 + lane) : null_rec<T>();
             __syncwarp();
             int myoff = -2;
             if (lane < cnt) {
-                const PtRec<T> rec = load_rec(a.recs + pstart + base + lane);
                 int xs0, ys0 = 0, zs0 = 0;
-                point_weights<T, DIM, NS>(a, rec, sc.ker + lane * G::KP, s_hc, xs0, ys0, zs0);
-                sc.c[lane] = cin[rec_index(rec)];
+                point_weights<T, DIM, NS>(a, rec_cur, sc.ker + lane * G::KP, s_hc, xs0, ys0, zs0);
+                sc.c[lane] = c_cur;
                 myoff = clampi(xs0 - ox, 0, a.ex - NS);
-                if (DIM > 1) myoff += clampi(ys0 - oy, 0, a.ey - NS) * a.sy;
-                if (DIM > 2) myoff += clampi(zs0 - oz, 0, a.ez - NS) * a.sz;
+                if (DIM > 1) { const int yo = clampi(ys0 - oy, 0, a.ey - NS); myoff += yo * a.sy; ylo = min(ylo, yo); yhi = max(yhi, yo); }
+                if (DIM > 2) { const int zo = clampi(zs0 - oz, 0, a.ez - NS); myoff += zo * a.sz; zlo = min(zlo, zo); zhi = max(zhi, zo); }
                 s_off[lane] = myoff;
             }
             __syncwarp();
@@ -264,20 +385,40 @@ spread_sm_kernel(const SIArgs<T> a)
                 int prev = __shfl_up_sync(0xffffffffu, myoff, 1);
                 if (lane == 0) prev = cur;
                 const unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && myoff != prev);
-                for (int q = 0; q < cnt; ++q) {
-                    if ((starts >> q) & 1u) {
-                        if (cur >= 0) flush_run();
-                        cur = s_off[q];
-                    }
-                    const T *kq = sc.ker + q * G::KP;
-                    const T k1 = active ? kq[ix] : (T)0;
-                    const C cv = sc.c[q];
-                    const T cr = cv.x * k1, ci = cv.y * k1;
+                if constexpr (G::PREFETCH) {
+                    // operands of point q are fetched one point ahead of their use
+                    T wq[G::NACC];
+                    load_row_weights<T, DIM, NS>(sc.ker, r, wq);
+                    T k1 = active ? sc.ker[ix] : (T)0;
+                    C cv = sc.c[0];
+                    for (int q = 0; q < cnt; ++q) {
+                        T wn[G::NACC];
+                        const int qn = q + 1 < cnt ? q + 1 : q;
+                        const T *kn = sc.ker + qn * G::KP;
+                        load_row_weights<T, DIM, NS>(kn, r, wn);
+                        const T k1n = active ? kn[ix] : (T)0;
+                        const C cvn = sc.c[qn];
+                        if ((starts >> q) & 1u) {
+                            if (cur >= 0) flush_run();
+                            cur = s_off[q];
+                        }
+                        acc.fma(cv.x * k1, cv.y * k1, wq);
 #pragma unroll
-                    for (int it = 0; it < G::ITERS; ++it) {
-                        const T wgt = row_weight<T, DIM, NS>(kq, it, r);
-                        acc[it].x = fma(cr, wgt, acc[it].x);
-                        acc[it].y = fma(ci, wgt, acc[it].y);
+                        for (int j = 0; j < G::NACC; ++j) wq[j] = wn[j];
+                        k1 = k1n; cv = cvn;
+                    }
+                } else {
+                    for (int q = 0; q < cnt; ++q) {
+                        const T *kq = sc.ker + q * G::KP;
+                        T wq[G::NACC];
+                        load_row_weights<T, DIM, NS>(kq, r, wq);
+                        const T k1 = active ? kq[ix] : (T)0;
+                        const C cv = sc.c[q];
+                        if ((starts >> q) & 1u) {
+                            if (cur >= 0) flush_run();
+                            cur = s_off[q];
+                        }
+                        acc.fma(cv.x * k1, cv.y * k1, wq);
                     }
                 }
             } else {
@@ -290,8 +431,10 @@ spread_sm_kernel(const SIArgs<T> a)
                     C *cell0 = tile + s_off[q] + ix;
 #pragma unroll 4
                     for (int it = 0; it < G::ITERS; ++it) {
-                        if (active && it * G::R + r < G::ROWS) {
-                            const T wgt = row_weight<T, DIM, NS>(kq, it, r);
+                        const int row = it * G::R + r;
+                        if (active && row < G::ROWS) {
+                            const int iz = row / NS, iy = row - iz * NS;
+                            const T wgt = DIM == 1 ? (T)1 : (DIM == 2 ? kq[G::NSX + r * G::WS + it] : kq[NS + iy] * kq[2 * NS + iz]);
                             C *cell = cell0 + tile_off(it);
                             C v = *cell;
                             v.x = fma(cr, wgt, v.x); v.y = fma(ci, wgt, v.y);
@@ -301,27 +444,37 @@ spread_sm_kernel(const SIArgs<T> a)
                     __syncwarp();
                 }
             }
+            rec_cur = rec_nxt; rec_nxt = rec_nn; c_cur = c_nxt;
         }
         if (cur >= 0) flush_run();
         __syncwarp();
 
-        // flush: vector RED of touched cells, single periodic wrap (reference guard
-        // ix < nf+pad, src/2d/spreadinterp2d.cu:222-224, is implied: cells past it stay zero)
+        // tile -> fine grid: vector RED over the touched rows only, clearing the tile on the way;
+        // single periodic wrap (reference guard ix < nf+pad, src/2d/spreadinterp2d.cu:222-224, is
+        // implied: cells past it are never touched and stay zero)
         {
-            int lx = lane, ly = 0, lz = 0;
-            while (lx >= a.sy) { lx -= a.sy; ++ly; }
-            for (int i = lane; i < a.tile_cells; i += 32) {
-                if (DIM > 2) { const int rows_per_z = a.sz / a.sy; while (ly >= rows_per_z) { ly -= rows_per_z; ++lz; } }
-                C v = tile[i];
-                if ((v.x != 0 || v.y != 0) && lx < a.ex) {
-                    int gx = wrap_index(ox + lx, a.nf1);
-                    size_t o = gx;
-                    if (DIM > 1) o += (size_t)wrap_index(oy + ly, a.nf2) * a.nf1;
-                    if (DIM > 2) o += (size_t)wrap_index(oz + lz, a.nf3) * a.nf1 * a.nf2;
-                    red_add(fwt + o, v.x, v.y);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+                zlo = min(zlo, __shfl_xor_sync(0xffffffffu, zlo, o)); zhi = max(zhi, __shfl_xor_sync(0xffffffffu, zhi, o));
+            }
+            const int y0 = DIM > 1 ? ylo : 0, ny = DIM > 1 ? yhi - ylo + NS : 1;
+            const int z0 = DIM > 2 ? zlo : 0, nz = DIM > 2 ? zhi - zlo + NS : 1;
+            for (int lz = z0; lz < z0 + nz; ++lz) {
+                size_t gz = 0;
+                if (DIM > 2) gz = (size_t)wrap_index(oz + lz, a.nf3) * a.nf1 * a.nf2;
+                for (int ly = y0; ly < y0 + ny; ++ly) {
+                    C *trow = tile + lz * a.sz + ly * a.sy;
+                    size_t gbase = gz;
+                    if (DIM > 1) gbase += (size_t)wrap_index(oy + ly, a.nf2) * a.nf1;
+                    for (int lx = lane; lx < a.ex; lx += 32) {
+                        const C v = trow[lx];
+                        if (v.x != 0 || v.y != 0) {
+                            red_add(fwt + gbase + wrap_index(ox + lx, a.nf1), v.x, v.y);
+                            trow[lx] = C{0, 0};
+                        }
+                    }
                 }
-                lx += 32;
-                while (lx >= a.sy) { lx -= a.sy; ++ly; }
             }
         }
         __syncwarp();
@@ -330,7 +483,7 @@ spread_sm_kernel(const SIArgs<T> a)
 
 // =============================================================================
 // GM / GM-sort spread: same lane-per-cell mapping and run accumulation, runs go straight
-// into the fine grid with vector RED (no tile).  Work unit = 32 consecutive points.
+// into the fine grid with vector RED (no tile).  Work unit = 256 consecutive points.
 // =============================================================================
 template <typename T, int DIM, int NS>
 __global__ void __launch_bounds__(256)
@@ -359,12 +512,10 @@ spread_gm_kernel(const SIArgs<T> a)
         const int n = (int)min((long long)(32 * CH), a.M - p0);
         const C *cin = a.c + (size_t)t * a.M;
         C *fwt = a.fw + (size_t)t * a.fwstride;
+        const PtRec<T> *recs = a.recs + p0;
 
-        C acc[G::MERGE ? G::ITERS : 1];
-        if (G::MERGE) {
-#pragma unroll
-            for (int it = 0; it < G::ITERS; ++it) { acc[it].x = 0; acc[it].y = 0; }
-        }
+        RunAcc<T, G::MERGE ? G::NACC : 1> acc;
+        acc.zero();
         int cx = 0, cy = 0, cz = 0;
         bool open = false;
 
@@ -374,26 +525,32 @@ spread_gm_kernel(const SIArgs<T> a)
 #pragma unroll
                 for (int it = 0; it < G::ITERS; ++it) {
                     const int row = it * G::R + r;
-                    if (active && row < G::ROWS && (acc[it].x != 0 || acc[it].y != 0)) {
+                    const C d = acc.get(it);
+                    if (active && row < G::ROWS && (d.x != 0 || d.y != 0)) {
                         size_t o = gx;
                         if (DIM == 2) o += (size_t)wrap_index(cy + row, a.nf2) * a.nf1;
                         if (DIM == 3) { const int iz = row / NS, iy = row - iz * NS;
                                         o += (size_t)wrap_index(cy + iy, a.nf2) * a.nf1 + (size_t)wrap_index(cz + iz, a.nf3) * plane; }
-                        red_add(fwt + o, acc[it].x, acc[it].y);
+                        red_add(fwt + o, d.x, d.y);
                     }
-                    acc[it].x = 0; acc[it].y = 0;
                 }
+                acc.zero();
             }
         };
 
+        PtRec<T> rec_cur = lane < n ? load_rec(recs + lane) : null_rec<T>();
+        PtRec<T> rec_nxt = 32 + lane < n ? load_rec(recs + 32 + lane) : null_rec<T>();
+        C c_cur = lane < n ? cin[rec_index(rec_cur)] : C{0, 0};
+
         for (int base = 0; base < n; base += 32) {
             const int cnt = min(32, n - base);
+            C c_nxt = base + 32 + lane < n ? cin[rec_index(rec_nxt)] : C{0, 0};
+            PtRec<T> rec_nn = base + 64 + lane < n ? load_rec(recs + base + 64 + lane) : null_rec<T>();
             __syncwarp();
             int mx = 0, my = 0, mz = 0;
             if (lane < cnt) {
-                const PtRec<T> rec = load_rec(a.recs + p0 + base + lane);
-                point_weights<T, DIM, NS>(a, rec, sc.ker + lane * G::KP, s_hc, mx, my, mz);
-                sc.c[lane] = cin[rec_index(rec)];
+                point_weights<T, DIM, NS>(a, rec_cur, sc.ker + lane * G::KP, s_hc, mx, my, mz);
+                sc.c[lane] = c_cur;
                 mx = clampi(mx, -a.nf1, a.nf1); my = clampi(my, -a.nf2, a.nf2); mz = clampi(mz, -a.nf3, a.nf3);
                 sc.x0[lane] = mx; sc.y0[lane] = my; sc.z0[lane] = mz;
             }
@@ -408,17 +565,14 @@ spread_gm_kernel(const SIArgs<T> a)
                 const C cv = sc.c[q];
                 const T cr = cv.x * k1, ci = cv.y * k1;
                 if constexpr (G::MERGE) {
+                    T wq[G::NACC];
+                    load_row_weights<T, DIM, NS>(kq, r, wq);
                     if ((starts >> q) & 1u) {
                         if (open) flush_run();
                         cx = sc.x0[q]; cy = sc.y0[q]; cz = sc.z0[q];
                         open = true;
                     }
-#pragma unroll
-                    for (int it = 0; it < G::ITERS; ++it) {
-                        const T wgt = row_weight<T, DIM, NS>(kq, it, r);
-                        acc[it].x = fma(cr, wgt, acc[it].x);
-                        acc[it].y = fma(ci, wgt, acc[it].y);
-                    }
+                    acc.fma(cr, ci, wq);
                 } else {
                     const int gx = wrap_index(sc.x0[q] + ix, a.nf1);
                     const int y0 = sc.y0[q], z0 = sc.z0[q];
@@ -426,16 +580,17 @@ spread_gm_kernel(const SIArgs<T> a)
                     for (int it = 0; it < G::ITERS; ++it) {
                         const int row = it * G::R + r;
                         if (active && row < G::ROWS) {
-                            const T wgt = row_weight<T, DIM, NS>(kq, it, r);
+                            const int iz = row / NS, iy = row - iz * NS;
+                            const T wgt = DIM == 1 ? (T)1 : (DIM == 2 ? kq[G::NSX + r * G::WS + it] : kq[NS + iy] * kq[2 * NS + iz]);
                             size_t o = gx;
                             if (DIM == 2) o += (size_t)wrap_index(y0 + row, a.nf2) * a.nf1;
-                            if (DIM == 3) { const int iz = row / NS, iy = row - iz * NS;
-                                            o += (size_t)wrap_index(y0 + iy, a.nf2) * a.nf1 + (size_t)wrap_index(z0 + iz, a.nf3) * plane; }
+                            if (DIM == 3) o += (size_t)wrap_index(y0 + iy, a.nf2) * a.nf1 + (size_t)wrap_index(z0 + iz, a.nf3) * plane;
                             red_add(fwt + o, cr * wgt, ci * wgt);
                         }
                     }
                 }
             }
+            rec_cur = rec_nxt; rec_nxt = rec_nn; c_cur = c_nxt;
         }
         if (open) flush_run();
         __syncwarp();
@@ -446,36 +601,10 @@ spread_gm_kernel(const SIArgs<T> a)
 // Interpolation: lanes over the stencil (lane = (row r, column ix)); the grid values of a run's
 // stencil are loaded once (coalesced row segments; points are sorted so neighbouring runs reuse
 // L1/L2 lines) and kept in registers for all points of the run.  Each lane accumulates its
-// column over the passes with the row weights (2 FMA per cell), scales by its x-weight once,
-// and the 32 partial sums of EIGHT points are reduced together by a transposing butterfly
-// (9 shuffles per component per 8 points instead of 40).  Result scattered to c[index].
+// column over the passes with the row weights (2 FMA per cell) and scales by its x-weight once;
+// the per-lane partial sums of 8 points are parked in shared memory [point][lane] and summed by
+// lane = (point, quarter) with two shuffle steps.  Result scattered to c[index].
 // =============================================================================
-template <typename T>
-__device__ __forceinline__ T reduce8(T (&v)[8], int lane)
-{
-    // after the call every lane holds the full sum of point  4*bit4 + 2*bit3 + bit2  of its lane id
-    bool up = lane & 16;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        T send = up ? v[j] : v[j + 4], keep = up ? v[j + 4] : v[j];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    up = lane & 8;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        T send = up ? v[j] : v[j + 2], keep = up ? v[j + 2] : v[j];
-        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    up = lane & 4;
-    {
-        T send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-    return v[0];
-}
-
 template <typename T, int DIM, int NS>
 __global__ void __launch_bounds__(256)
 interp_kernel(const SIArgs<T> a)
@@ -496,6 +625,8 @@ interp_kernel(const SIArgs<T> a)
     const long long total = nchunk * a.nt;
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
     const size_t plane = (size_t)a.nf1 * a.nf2;
+    constexpr int RS = 34;                             // row stride of the reduction buffer (cells)
+    const int rp = lane >> 2, rq = lane & 3;           // reduction role: point rp of the group, quarter rq
 
     for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp; w < total; w += wstride) {
         const int t = (int)(w / nchunk);
@@ -503,8 +634,9 @@ interp_kernel(const SIArgs<T> a)
         const int n = (int)min((long long)(32 * CH), a.M - p0);
         C *cout = a.c + (size_t)t * a.M;
         const C *fwt = a.fw + (size_t)t * a.fwstride;
+        const PtRec<T> *recs = a.recs + p0;
 
-        C v[G::MERGE ? G::ITERS : 1];
+        C v[G::MERGE ? G::NACC : 1];
         int cx = 0, cy = 0, cz = 0;
         bool open = false;
 
@@ -512,10 +644,10 @@ interp_kernel(const SIArgs<T> a)
             if constexpr (G::MERGE) {
                 const C *col = fwt + wrap_index(cx + ix, a.nf1);
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it) {
+                for (int it = 0; it < G::NACC; ++it) {
                     const int row = it * G::R + r;
                     v[it].x = 0; v[it].y = 0;
-                    if (active && row < G::ROWS) {
+                    if (it < G::ITERS && active && row < G::ROWS) {
                         size_t o = 0;
                         if (DIM == 2) o = (size_t)wrap_index(cy + row, a.nf2) * a.nf1;
                         if (DIM == 3) { const int iz = row / NS, iy = row - iz * NS;
@@ -526,14 +658,17 @@ interp_kernel(const SIArgs<T> a)
             }
         };
 
+        PtRec<T> rec_cur = lane < n ? load_rec(recs + lane) : null_rec<T>();
+        PtRec<T> rec_nxt = 32 + lane < n ? load_rec(recs + 32 + lane) : null_rec<T>();
+
         for (int base = 0; base < n; base += 32) {
             const int cnt = min(32, n - base);
+            PtRec<T> rec_nn = base + 64 + lane < n ? load_rec(recs + base + 64 + lane) : null_rec<T>();
             __syncwarp();
             int mx = 0, my = 0, mz = 0;
             if (lane < cnt) {
-                const PtRec<T> rec = load_rec(a.recs + p0 + base + lane);
-                point_weights<T, DIM, NS>(a, rec, sc.ker + lane * G::KP, s_hc, mx, my, mz);
-                s_idx[lane] = rec_index(rec);
+                point_weights<T, DIM, NS>(a, rec_cur, sc.ker + lane * G::KP, s_hc, mx, my, mz);
+                s_idx[lane] = rec_index(rec_cur);
                 mx = clampi(mx, -a.nf1, a.nf1); my = clampi(my, -a.nf2, a.nf2); mz = clampi(mz, -a.nf3, a.nf3);
                 sc.x0[lane] = mx; sc.y0[lane] = my; sc.z0[lane] = mz;
             }
@@ -544,53 +679,60 @@ interp_kernel(const SIArgs<T> a)
             const unsigned starts = G::MERGE ? __ballot_sync(0xffffffffu, lane < cnt && differs) : 0xffffffffu;
 
             for (int q0 = 0; q0 < cnt; q0 += 8) {
-                T accr[8], acci[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    accr[j] = 0; acci[j] = 0;
+                const int gcnt = min(8, cnt - q0);
+#pragma unroll 1
+                for (int j = 0; j < gcnt; ++j) {
                     const int q = q0 + j;
-                    if (q < cnt) {
-                        const T *kq = sc.ker + q * G::KP;
-                        T sr = 0, si = 0;
-                        if constexpr (G::MERGE) {
-                            if ((starts >> q) & 1u) {
-                                cx = sc.x0[q]; cy = sc.y0[q]; cz = sc.z0[q];
-                                open = true;
-                                load_run();
-                            }
+                    const T *kq = sc.ker + q * G::KP;
+                    T sr = 0, si = 0;
+                    if constexpr (G::MERGE) {
+                        if ((starts >> q) & 1u) {
+                            cx = sc.x0[q]; cy = sc.y0[q]; cz = sc.z0[q];
+                            open = true;
+                            load_run();
+                        }
+                        T wq[G::NACC];
+                        load_row_weights<T, DIM, NS>(kq, r, wq);
 #pragma unroll
-                            for (int it = 0; it < G::ITERS; ++it) {
-                                const T wgt = row_weight<T, DIM, NS>(kq, it, r);
-                                sr = fma(v[it].x, wgt, sr);
-                                si = fma(v[it].y, wgt, si);
-                            }
-                        } else {
-                            const C *col = fwt + wrap_index(sc.x0[q] + ix, a.nf1);
-                            const int y0 = sc.y0[q], z0 = sc.z0[q];
+                        for (int it = 0; it < G::NACC; ++it) {
+                            sr = fma(v[it].x, wq[it], sr);
+                            si = fma(v[it].y, wq[it], si);
+                        }
+                    } else {
+                        const C *col = fwt + wrap_index(sc.x0[q] + ix, a.nf1);
+                        const int y0 = sc.y0[q], z0 = sc.z0[q];
 #pragma unroll 4
-                            for (int it = 0; it < G::ITERS; ++it) {
-                                const int row = it * G::R + r;
-                                if (row < G::ROWS) {
-                                    const T wgt = row_weight<T, DIM, NS>(kq, it, r);
-                                    size_t o = 0;
-                                    if (DIM == 2) o = (size_t)wrap_index(y0 + row, a.nf2) * a.nf1;
-                                    if (DIM == 3) { const int iz = row / NS, iy = row - iz * NS;
-                                                    o = (size_t)wrap_index(y0 + iy, a.nf2) * a.nf1 + (size_t)wrap_index(z0 + iz, a.nf3) * plane; }
-                                    const C g = col[o];
-                                    sr = fma(g.x, wgt, sr);
-                                    si = fma(g.y, wgt, si);
-                                }
+                        for (int it = 0; it < G::ITERS; ++it) {
+                            const int row = it * G::R + r;
+                            if (active && row < G::ROWS) {
+                                const int iz = row / NS, iy = row - iz * NS;
+                                const T wgt = DIM == 1 ? (T)1 : (DIM == 2 ? kq[G::NSX + r * G::WS + it] : kq[NS + iy] * kq[2 * NS + iz]);
+                                size_t o = 0;
+                                if (DIM == 2) o = (size_t)wrap_index(y0 + row, a.nf2) * a.nf1;
+                                if (DIM == 3) o = (size_t)wrap_index(y0 + iy, a.nf2) * a.nf1 + (size_t)wrap_index(z0 + iz, a.nf3) * plane;
+                                const C g = col[o];
+                                sr = fma(g.x, wgt, sr);
+                                si = fma(g.y, wgt, si);
                             }
                         }
-                        const T k1 = active ? kq[ix] : (T)0;
-                        accr[j] = sr * k1; acci[j] = si * k1;
                     }
+                    const T k1 = active ? kq[ix] : (T)0;
+                    sc.red[j * RS + lane] = C{sr * k1, si * k1};
                 }
-                const T tr = reduce8(accr, lane), ti = reduce8(acci, lane);
-                // lane bits (4,3,2) select the point in reduce8's order: 4*bit4 + 2*bit3 + bit2
-                const int qsel = q0 + (((lane >> 4) & 1) << 2) + (((lane >> 3) & 1) << 1) + ((lane >> 2) & 1);
-                if ((lane & 3) == 0 && qsel < cnt) { C o; o.x = tr; o.y = ti; cout[s_idx[qsel]] = o; }
+                __syncwarp();
+                // lane (rp, rq) sums lanes [8 rq, 8 rq + 8) of point rp, then two butterfly steps
+                T tr = 0, ti = 0;
+                if (rp < gcnt) {
+                    const C *src = sc.red + rp * RS + rq * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const C g = src[i]; tr += g.x; ti += g.y; }
+                }
+                tr += __shfl_xor_sync(0xffffffffu, tr, 1); ti += __shfl_xor_sync(0xffffffffu, ti, 1);
+                tr += __shfl_xor_sync(0xffffffffu, tr, 2); ti += __shfl_xor_sync(0xffffffffu, ti, 2);
+                if (rq == 0 && rp < gcnt) cout[s_idx[q0 + rp]] = C{tr, ti};
+                __syncwarp();
             }
+            rec_cur = rec_nxt; rec_nxt = rec_nn;
         }
         __syncwarp();
     }
