@@ -94,6 +94,7 @@ for _sfx, _real in (("", c_double), ("f", c_float)):
         set_timing=_bind("cufinufft%s_set_timing" % _sfx, [c_void_p, c_int]),
         get_timing=_bind("cufinufft%s_get_timing" % _sfx, [c_void_p, c_void_p]),
         get_launch_counts=_bind("cufinufft%s_get_launch_counts" % _sfx, [c_void_p, c_void_p]),
+        set_interp_engine=_bind("cufinufft%s_set_interp_engine" % _sfx, [c_void_p, c_int]),
     )
 
 # reference-compatible module-level names
@@ -114,4 +115,4 @@ C_ABI_SYMBOLS = [base % s for s in ("", "f") for base in (
 EXTENSION_SYMBOLS = ["cufinufft_b200_version", "cufinufft_b200_host_params", "cufinufft_b200_phihat_quadrature"] + [base % s for s in ("", "f") for base in (
     "cufinufft%s_set_stream", "cufinufft%s_setpts_host", "cufinufft%s_execute_host", "cufinufft%s_spread",
     "cufinufft%s_interp", "cufinufft%s_get_ints", "cufinufft%s_get_reals", "cufinufft%s_set_timing",
-    "cufinufft%s_get_timing", "cufinufft%s_get_launch_counts")]
+    "cufinufft%s_get_timing", "cufinufft%s_get_launch_counts", "cufinufft%s_set_interp_engine")]

@@ -96,6 +96,7 @@ struct Plan {
     int tile_sy = 0, tile_sz = 0;        // padded strides (cells)
     int tile_cells = 0;
     int sm_warps = 0;                    // warps per block for the SM spread kernel (0 = SM unusable)
+    int interp_engine = 0;               // 0 auto (tile when sorted and it fits), 1 gather, 2 tile
     // timing / accounting
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

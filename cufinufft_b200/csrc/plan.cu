@@ -520,6 +520,8 @@ int cufinufft_set_timing(cufinufft_plan plan, int on) { if (!PD(plan)) return CF
 int cufinufftf_set_timing(cufinufftf_plan plan, int on) { if (!PD(plan)) return CFB_ERR_BAD_ARG; plan->p->timing = on != 0; return 0; }
 int cufinufft_get_timing(cufinufft_plan plan, float *out) { return cfb::get_timing<double>(PD(plan), out); }
 int cufinufftf_get_timing(cufinufftf_plan plan, float *out) { return cfb::get_timing<float>(PD(plan), out); }
+int cufinufft_set_interp_engine(cufinufft_plan plan, int e) { if (!PD(plan) || e < 0 || e > 2) return CFB_ERR_BAD_ARG; plan->p->interp_engine = e; return 0; }
+int cufinufftf_set_interp_engine(cufinufftf_plan plan, int e) { if (!PD(plan) || e < 0 || e > 2) return CFB_ERR_BAD_ARG; plan->p->interp_engine = e; return 0; }
 int cufinufft_get_launch_counts(cufinufft_plan plan, int *o) { if (!PD(plan) || !o) return CFB_ERR_BAD_ARG; o[0] = plan->p->launches_setpts; o[1] = plan->p->launches_exec; return 0; }
 int cufinufftf_get_launch_counts(cufinufftf_plan plan, int *o) { if (!PD(plan) || !o) return CFB_ERR_BAD_ARG; o[0] = plan->p->launches_setpts; o[1] = plan->p->launches_exec; return 0; }
 

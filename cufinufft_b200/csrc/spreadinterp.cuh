@@ -738,6 +738,162 @@ interp_kernel(const SIArgs<T> a)
     }
 }
 
+// =============================================================================
+// Tile interpolation (replaces Interp_{2,3}d_Subprob[_Horner], src/2d/spreadinterp2d.cu:597-745,
+// src/3d/spreadinterp3d.cu:760-948, and serves the sorted NUptsdriven requests as well).
+// Work item = one subproblem (bin, <= maxsubprobsize sorted points) of one transform, pulled from
+// a global counter by persistent BLOCKS.  The bin's fine-grid tile with its ceil(ns/2) halo is
+// copied global -> shared with cp.async (LDGSTS, no register staging, periodic wrap resolved per
+// row) while every thread already evaluates the kernel weights of its first point.  Then
+// THREAD-PER-POINT: the d*ns weights stay in registers, the ns^d stencil is read from the tile
+// with one LDS per complex cell (points are sorted by stencil origin inside the bin, so the lanes
+// of a warp read the same or neighbouring cells: broadcast / conflict-free) and accumulated
+// separably (2 FMA per cell + 2 per row + 2 per plane).  No atomics, no shuffles, no scratch.
+// Tile layout [ez][ey][ex] complex, x fastest, unpadded.
+// =============================================================================
+__device__ __forceinline__ void cp_async_cell(float2 *dst, const float2 *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_cell(double2 *dst, const double2 *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename T, int DIM, int NS> struct TileInterp {
+    static constexpr bool ROLL_Z = DIM == 3 && NS >= 8;      // plane loop rolled (kz indexed dynamically)
+};
+
+template <typename T, int DIM, int NS>
+__global__ void __launch_bounds__(512)
+interp_tile_kernel(const SIArgs<T> a)
+{
+    using C = typename cplx_of<T>::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    T *s_hc = reinterpret_cast<T *>(smem);
+    C *tile = reinterpret_cast<C *>(smem + 18 * 16 * sizeof(T));
+    __shared__ long long s_work;
+    stage_horner<T, NS>(a, s_hc);
+
+    const int nsub = a.scalars[0];
+    const long long total = (long long)nsub * a.nt;
+    const int ex = a.ex, ey = a.ey, ez = a.ez;
+    const int rows = ey * ez;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const size_t plane = (size_t)a.nf1 * a.nf2;
+
+    for (;;) {
+        __syncthreads();                                  // everybody is done with the previous tile
+        if (threadIdx.x == 0) s_work = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const long long w = s_work;
+        if (w >= total) break;
+        const int t = (int)(w / nsub), s = (int)(w - (long long)t * nsub);
+        const int bin = a.s2b[s];
+        const int k = s - a.substart[bin];
+        const int pstart = a.binstart[bin] + k * a.maxsub;
+        const int n = min(a.maxsub, a.binsize[bin] - k * a.maxsub);
+        const int b1 = bin % a.nb1, b23 = bin / a.nb1;
+        const int b2 = DIM > 1 ? b23 % a.nb2 : 0, b3 = DIM > 2 ? b23 / a.nb2 : 0;
+        const int ox = b1 * a.bs1 - a.pad, oy = b2 * a.bs2 - a.pad, oz = b3 * a.bs3 - a.pad;
+        C *cout = a.c + (size_t)t * a.M;
+        const C *fwt = a.fw + (size_t)t * a.fwstride;
+        const PtRec<T> *recs = a.recs + pstart;
+
+        // ---- tile <- fine grid (async); rows are distributed over the warps
+        for (int row = warp; row < rows; row += nwarps) {
+            const int lz = DIM > 2 ? row / ey : 0, ly = row - lz * ey;
+            int gy = 0, gz = 0;
+            bool ok = true;
+            if (DIM > 1) { gy = wrap_index(oy + ly, a.nf2); ok = ok && gy >= 0 && gy < a.nf2; }
+            if (DIM > 2) { gz = wrap_index(oz + lz, a.nf3); ok = ok && gz >= 0 && gz < a.nf3; }
+            if (!ok) continue;                            // beyond nf + pad on a grid smaller than the bin: never read
+            const C *grow = fwt + (size_t)gz * plane + (size_t)gy * a.nf1;
+            C *trow = tile + (size_t)row * ex;
+            for (int lx = lane; lx < ex; lx += 32) {
+                const int gx = wrap_index(ox + lx, a.nf1);
+                if (gx >= 0 && gx < a.nf1) cp_async_cell(trow + lx, grow + gx);
+            }
+        }
+
+        // ---- thread-per-point
+        bool first = true;
+        for (int i = threadIdx.x; i < n || first; i += blockDim.x) {
+            const bool valid = i < n;
+            T kx[NS], ky[DIM > 1 ? NS : 1], kz[DIM > 2 ? NS : 1];
+            int off = 0, idx = 0;
+            if (valid) {
+                const PtRec<T> rec = load_rec(recs + i);
+                idx = rec_index(rec);
+                const int xs = stencil_start(rec.x, NS);
+                kernel_vector<T, NS, true>(kx, (T)xs - rec.x, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+                off = clampi(xs - ox, 0, ex - NS);
+                if (DIM > 1) {
+                    const int ys = stencil_start(rec.y, NS);
+                    kernel_vector<T, NS, true>(ky, (T)ys - rec.y, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+                    off += clampi(ys - oy, 0, ey - NS) * ex;
+                }
+                if (DIM > 2) {
+                    const int zs = stencil_start(rec.z, NS);
+                    kernel_vector<T, NS, true>(kz, (T)zs - rec.z, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+                    off += clampi(zs - oz, 0, ez - NS) * ex * ey;
+                }
+            }
+            if (first) {                                  // the tile has landed (weights of the first point overlapped the copy)
+                cp_async_wait_all();
+                __syncthreads();
+                first = false;
+            }
+            if (!valid) continue;
+            const C *base = tile + off;
+            T ar = 0, ai = 0;
+            if constexpr (DIM == 1) {
+#pragma unroll
+                for (int ix = 0; ix < NS; ++ix) { const C g = base[ix]; ar = fma(kx[ix], g.x, ar); ai = fma(kx[ix], g.y, ai); }
+            } else if constexpr (DIM == 2) {
+#pragma unroll
+                for (int iy = 0; iy < NS; ++iy) {
+                    const C *rowp = base + iy * ex;
+                    T rr = 0, ri = 0;
+#pragma unroll
+                    for (int ix = 0; ix < NS; ++ix) { const C g = rowp[ix]; rr = fma(kx[ix], g.x, rr); ri = fma(kx[ix], g.y, ri); }
+                    ar = fma(ky[iy], rr, ar); ai = fma(ky[iy], ri, ai);
+                }
+            } else {
+                const int sz = ex * ey;
+                auto plane_sum = [&](const C *pl, T &pr, T &pi) {
+                    pr = 0; pi = 0;
+#pragma unroll
+                    for (int iy = 0; iy < NS; ++iy) {
+                        const C *rowp = pl + iy * ex;
+                        T rr = 0, ri = 0;
+#pragma unroll
+                        for (int ix = 0; ix < NS; ++ix) { const C g = rowp[ix]; rr = fma(kx[ix], g.x, rr); ri = fma(kx[ix], g.y, ri); }
+                        pr = fma(ky[iy], rr, pr); pi = fma(ky[iy], ri, pi);
+                    }
+                };
+                if constexpr (TileInterp<T, DIM, NS>::ROLL_Z) {
+#pragma unroll 1
+                    for (int iz = 0; iz < NS; ++iz) {
+                        T pr, pi;
+                        plane_sum(base + iz * sz, pr, pi);
+                        ar = fma(kz[iz], pr, ar); ai = fma(kz[iz], pi, ai);
+                    }
+                } else {
+#pragma unroll
+                    for (int iz = 0; iz < NS; ++iz) {
+                        T pr, pi;
+                        plane_sum(base + iz * sz, pr, pi);
+                        ar = fma(kz[iz], pr, ar); ai = fma(kz[iz], pi, ai);
+                    }
+                }
+            }
+            cout[idx] = C{ar, ai};
+        }
+    }
+}
+
 // ---- host-side launch helpers (one instantiation per (T, DIM) translation unit) ----
 template <typename T, int DIM> int launch_spread(Plan<T> &p, const typename Plan<T>::C *c, typename Plan<T>::C *fw, int nt);
 template <typename T, int DIM> int launch_interp(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *fw, int nt);

@@ -62,9 +62,38 @@ static int do_spread(Plan<T> &p, SIArgs<T> &a)
     return 0;
 }
 
+// Tile engine (interp_tile_kernel): used whenever the points are bin-sorted and the bin tile
+// with its halo fits in shared memory; the gather engine (interp_kernel) serves the rest
+// (gpu_sort = 0, very wide 3-D fp64 stencils).  p.interp_engine: 0 auto, 1 gather, 2 tile.
+template <typename T, int DIM, int NS>
+static int do_interp_tile(Plan<T> &p, SIArgs<T> &a, bool &done)
+{
+    using C = typename Plan<T>::C;
+    done = false;
+    if (!p.sorted || p.interp_engine == 1) return 0;
+    const size_t head = 18 * 16 * sizeof(T);
+    const size_t cells = (size_t)a.ex * a.ey * a.ez;
+    const size_t smem = head + cells * sizeof(C);
+    if (smem + 1024 > (size_t)p.max_smem_optin) return 0;
+    const int threads = smem > 96 * 1024 ? 512 : 256;
+    CFB_CUDA_OK(cudaFuncSetAttribute(interp_tile_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CFB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, interp_tile_kernel<T, DIM, NS>, threads, smem));
+    if (occ < 1) return 0;
+    CFB_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(int), p.stream));
+    interp_tile_kernel<T, DIM, NS><<<p.num_sms * occ, threads, smem, p.stream>>>(a);
+    p.launches_exec++;
+    CFB_CUDA_OK(cudaGetLastError());
+    done = true;
+    return 0;
+}
+
 template <typename T, int DIM, int NS>
 static int do_interp(Plan<T> &p, SIArgs<T> &a)
 {
+    bool done = false;
+    if (int e = do_interp_tile<T, DIM, NS>(p, a, done)) return e;
+    if (done) return 0;
     const size_t head = 18 * 16 * sizeof(T);
     const int warps = 8;
     size_t smem = head + warps * warp_scratch_bytes<T, DIM, NS>();
@@ -82,14 +111,22 @@ template <typename T> struct max_ns;
 template <> struct max_ns<float>  { static constexpr int v = 9; };   // tol clamps at 6e-8 -> ns <= 9
 template <> struct max_ns<double> { static constexpr int v = 16; };
 
+// development builds (make EXTRA=-DCFB_DEV_NS) instantiate only the widths of the five
+// BASELINE.json configs and the smoke test; the other widths then return error 10
+#ifdef CFB_DEV_NS
+constexpr bool ns_enabled(int ns) { return ns == 4 || ns == 5 || ns == 6 || ns == 7 || ns == 10 || ns == 11 || ns == 13; }
+#else
+constexpr bool ns_enabled(int) { return true; }
+#endif
+
 template <typename T, int DIM, int NS>
 struct NsDispatch {
     static int spread(Plan<T> &p, SIArgs<T> &a) {
-        if (p.ns == NS) return do_spread<T, DIM, NS>(p, a);
+        if constexpr (ns_enabled(NS)) { if (p.ns == NS) return do_spread<T, DIM, NS>(p, a); }
         return NsDispatch<T, DIM, NS - 1>::spread(p, a);
     }
     static int interp(Plan<T> &p, SIArgs<T> &a) {
-        if (p.ns == NS) return do_interp<T, DIM, NS>(p, a);
+        if constexpr (ns_enabled(NS)) { if (p.ns == NS) return do_interp<T, DIM, NS>(p, a); }
         return NsDispatch<T, DIM, NS - 1>::interp(p, a);
     }
     static size_t scratch(int ns) {

@@ -158,6 +158,11 @@ class cufinufft:
             raise RuntimeError('No timing recorded.')
         return dict(zip(("spread_interp_ms", "fft_ms", "deconv_amplify_ms", "memset_ms", "total_ms"), list(t)))
 
+    def set_interp_engine(self, engine):
+        """0 automatic, 1 gather engine, 2 shared-memory tile engine (include/cufinufft_b200.h)."""
+        if self._fn["set_interp_engine"](self.plan, int(engine)) != 0:
+            raise RuntimeError('Error selecting the interpolation engine.')
+
     def launch_counts(self):
         n = (c_int * 2)()
         self._fn["get_launch_counts"](self.plan, n)

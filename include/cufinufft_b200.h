@@ -94,6 +94,12 @@ int cufinufft_set_timing(cufinufft_plan plan, int on);
 int cufinufftf_set_timing(cufinufftf_plan plan, int on);
 int cufinufft_get_timing(cufinufft_plan plan, float *out);
 int cufinufftf_get_timing(cufinufftf_plan plan, float *out);
+/* Interpolation engine: 0 = automatic (the shared-memory tile engine whenever the points are
+ * bin-sorted and the bin tile with its halo fits in shared memory, else the gather engine),
+ * 1 = gather engine (reference Interp_*_NUptsdriven schedule), 2 = tile engine when possible
+ * (reference Interp_*_Subprob schedule).  Results agree to rounding; this is an A/B switch. */
+int cufinufft_set_interp_engine(cufinufft_plan plan, int engine);
+int cufinufftf_set_interp_engine(cufinufftf_plan plan, int engine);
 /* number of kernels this library launched in the last setpts / execute (bench.py's gpu_launches) */
 int cufinufft_get_launch_counts(cufinufft_plan plan, int *out2);
 int cufinufftf_get_launch_counts(cufinufftf_plan plan, int *out2);
