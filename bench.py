@@ -39,9 +39,9 @@ CONFIGS = {
             M=100_000_000, tol=1e-5, dtype="float32", dist="blobs", ntransf=1, opts=dict(gpu_method=2)),
     4: dict(name="cfg4: 2D type 1 fp32 512x512 radial M=262144 ntransf=64 tol=1e-4", type=1, modes=(512, 512),
             M=262_144, tol=1e-4, dtype="float32", dist="radial", ntransf=64, opts=dict(gpu_method=2), maxbatch=0),
-    5: dict(name="cfg5(1/8): 3D type 2 fp64 512^3 M=1.25e8 uniform tol=1e-9 (per-GPU share of M=1e9)", type=2,
-            modes=(512, 512, 512), M=125_000_000, tol=1e-9, dtype="float64", dist="uniform", ntransf=1,
-            opts=dict(gpu_method=1, gpu_sort=1)),
+    5: dict(name="cfg5: 3D type 2 fp64 512^3 (1024^3 fine grid) M=1e9 uniform tol=1e-9, z-slab partitioned", type=2,
+            modes=(512, 512, 512), M=1_000_000_000, tol=1e-9, dtype="float64", dist="uniform", ntransf=1,
+            opts=dict(gpu_method=1, gpu_sort=1), slab=True),
 }
 
 
@@ -161,6 +161,10 @@ def cpu_baseline(cfg, seconds_budget=15.0):
     """The oracle port on the host cores: fixed part (amplify|deconvolve + FFT) timed once,
     spread|interp timed on a bounded sample and extrapolated linearly in M."""
     from oracle import oracle as orc
+    if cfg.get("slab") and int(np.prod(cfg["modes"])) > 128 ** 3:
+        # config 5 on the host: the 1024^3 fine grid (17 GB) + numpy FFT does not fit the time box --
+        # the point-proportional part is timed on a 128^3-mode problem and extrapolated in M
+        cfg = dict(cfg, modes=(128, 128, 128))
     dt = np.dtype(cfg["dtype"])
     cd = np.complex64 if dt == np.float32 else np.complex128
     modes, dim = cfg["modes"], len(cfg["modes"])
@@ -224,6 +228,159 @@ def run_reference_impl(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_slab(args, cfg, rank, local_rank, world):
+    """Config 5: ONE 3-D type-2 transform, fine grid split into z-slabs over the ranks (strong
+    scaling: M and the grid are fixed, every rank gets M/world points inside its slab and a
+    replicated mode array).  Type 2 needs no collective (csrc/slab.cu)."""
+    import torch
+    import torch.distributed as dist
+    from cufinufft_b200.multi import SlabPlan, slab_type2
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    npdt, tdt, cdt = np.dtype("float64"), torch.float64, torch.complex128
+    shape = tuple(cfg["modes"])[::-1]
+    M_total = cfg["M"]
+    M = M_total // world + (1 if rank < M_total % world else 0)
+    stream = torch.cuda.current_stream()
+    plan = SlabPlan(2, shape, eps=cfg["tol"], dtype=npdt, rank=rank, world=world, gpu_device_id=local_rank, **cfg["opts"])
+    plan.set_stream(stream.cuda_stream)
+    geo = plan.info()
+    nf3, z0, z1 = geo["nf3"], geo["z0"], geo["z1"]
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242 + rank)
+    x = (torch.rand(M, generator=g, device=dev, dtype=tdt) * 2 - 1) * np.pi
+    y = (torch.rand(M, generator=g, device=dev, dtype=tdt) * 2 - 1) * np.pi
+    z = ((torch.rand(M, generator=g, device=dev, dtype=tdt) * ((z1 - z0) * (1 - 1e-12)) + z0) / nf3 - 0.5) * (2 * np.pi)
+    gk = torch.Generator(device=dev)
+    gk.manual_seed(7)                                   # the mode array is REPLICATED: same seed on every rank
+    fk = torch.view_as_complex((torch.rand(shape + (2,), generator=gk, device=dev, dtype=tdt) * 2 - 1).contiguous())
+    c = torch.zeros(M, dtype=cdt, device=dev)
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    plan.set_pts(z, y, x)
+    torch.cuda.synchronize()
+    t_set = []
+    for _ in range(3):
+        ev[0].record(stream)
+        plan.set_pts(z, y, x)
+        ev[1].record(stream)
+        torch.cuda.synchronize()
+        t_set.append(ev[0].elapsed_time(ev[1]))
+    setpts_ms = float(np.median(t_set))
+    outside = plan.info()["outside"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    plan.set_timing(True)
+    for _ in range(args.warmup):
+        slab_type2(plan, c, fk)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        slab_type2(plan, c, fk)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = plan.launch_counts()["execute"] * args.steps
+    stage_ms = []
+    for _ in range(min(args.steps, 3)):
+        slab_type2(plan, c, fk)
+        stage_ms.append(plan.timing())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    clocks = sampler.summary()
+    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step = float(tt.item()) / args.steps
+    value = M_total / (ms_step * 1e-3)
+    checksum = float(torch.view_as_real(c).abs().sum().item())
+
+    e2e = None
+    try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
+        fk_host = torch.empty(shape, dtype=cdt, pin_memory=True)
+        c_host = torch.empty(M, dtype=cdt, pin_memory=True)
+        fk_host.copy_(fk)
+        fk_dev = torch.empty_like(fk)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            fk_dev.copy_(fk_host, non_blocking=True)
+            slab_type2(plan, c, fk_dev)
+            c_host.copy_(c, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_step()
+        barrier()
+        ksteps = 2
+        e0.record(stream)
+        for _ in range(ksteps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms_e2e = float(te.item()) / ksteps
+        e2e = {"value": M_total / (ms_e2e * 1e-3), "unit": "NU pts/s", "h2d_bytes_per_step": fk_host.numel() * 16,
+               "d2h_bytes_per_step": c_host.numel() * 16, "ms_per_step": ms_e2e,
+               "api": "per rank: pinned host fk -> device, cufinufft_slab_type2 (C ABI), c -> pinned host"}
+    except Exception as exc:   # noqa: BLE001
+        e2e = {"value": None, "error": repr(exc)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    k_ms = float(np.median([s["spread_interp_ms"] for s in stage_ms]))
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    local_cells = geo["nz_local"] * geo["plane_cells"]
+    abytes = M * (3 * 8 + 16 + 4) + local_cells * 16
+    achieved = abytes / (k_ms * 1e-3) / 1e9
+    stages = {k: float(np.median([s[k] for s in stage_ms])) for k in stage_ms[0]}
+    line = {
+        "metric": "NU points/s per execute", "value": value, "unit": "NU pts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["name"], "type": 2, "modes": list(cfg["modes"]), "M_total": M_total, "M_per_gpu": M,
+                   "tol": cfg["tol"], "ns": geo["ns"], "fine_grid": [geo["nf1"], geo["nf2"], nf3],
+                   "slab_planes_rank0": [z0, z1], "halo_planes": geo["pad"], "points_outside_slab": outside,
+                   "l2": "inputs larger than L2 (no flush needed)",
+                   "parallelism": "z-slab decomposition of the fine grid, points pre-binned by slab, mode array "
+                                  "replicated; type 2: no collective (halo planes are derived locally)"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "interp", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": abytes, "kernel_ms": k_ms,
+                     "note": "rank 0's interp launch; HBM roofline as the contract asks, the binding resource is the FP64 pipe "
+                             "and shared-memory bandwidth (DESIGN.md)"},
+        "stages_ms": stages, "setpts": {"ms": setpts_ms, "pts_per_s": M / (setpts_ms * 1e-3)},
+        "checksum_abs_c_rank0": checksum, "cpu_baseline": None,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_baseline(cfg)
+        cb["sample"] = "fine grid down-scaled to 128^3 modes on the host: " + cb["sample"]
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,6 +410,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    if cfg.get("slab"):
+        run_slab(args, cfg, rank, local_rank, world)
+        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

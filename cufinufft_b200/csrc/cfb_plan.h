@@ -49,6 +49,10 @@ struct SortGeo {
     int nk[3];      // distinct stencil origins per bin and dimension (1 = key is the bin alone)
     int cpb;        // nk[0]*nk[1]*nk[2]
     int ns;
+    // z-slab plans (slab.cu): z is rescaled on the GLOBAL fine grid nfz and binned in slab-local
+    // planes zl = z_r - zshift; nf[2] is then the local plane count.  Ordinary plans: nfz = nf[2],
+    // zshift = 0, zlo = 0, zhi = nf[2].
+    int nfz, zshift, zlo, zhi;
 };
 
 template <typename T>
@@ -97,12 +101,22 @@ struct Plan {
     int tile_cells = 0;
     int sm_warps = 0;                    // warps per block for the SM spread kernel (0 = SM unusable)
     int interp_engine = 0;               // 0 auto (tile when sorted and it fits), 1 gather, 2 tile
+    // z-slab decomposition of one 3-D transform (slab.cu): this plan owns the fine-grid
+    // planes [z0, z1) of a global grid with nf3g planes and holds them with `tile_pad` halo planes on
+    // both sides: nf3 = z1 - z0 + 2*tile_pad local planes, local plane l = global plane zshift + l.
+    bool slab = false;
+    int nf3g = 0, z0 = 0, z1 = 0, zshift = 0;
+    int slab_rank = 0, slab_world = 1;
+    cufftHandle fft2d = 0, fftz = 0;     // batched (x,y) planes of the local grid; strided z pencils of zbuf
+    bool have_fft2d = false, have_fftz = false;
+    DevBuf zbuf;                         // C[nf3g][mt][ms]: mode columns, all z planes (z-pencil layout)
     // timing / accounting
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int launches_setpts = 0, launches_exec = 0;
 
     size_t grid_cells() const { return (size_t)nf1 * nf2 * nf3; }
+    int nf3_global() const { return slab ? nf3g : nf3; }
     size_t nmodes() const { return (size_t)ms * mt * mu; }
 };
 
@@ -124,6 +138,13 @@ template <typename T> int stage_interp(Plan<T> &p, typename Plan<T>::C *c, const
 template <typename T> int stage_deconvolve(Plan<T> &p, typename Plan<T>::C *fk, const typename Plan<T>::C *fw, int nt);
 template <typename T> int stage_amplify(Plan<T> &p, const typename Plan<T>::C *fk, typename Plan<T>::C *fw, int nt);
 template <typename T> void plan_tile_geometry(Plan<T> &p);                 // spread.cu
+// z-slab stages (slab.cu)
+template <typename T> int slab_make_ffts(Plan<T> &p);
+template <typename T> int slab_type2(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *fk);
+template <typename T> int slab_type1_spread(Plan<T> &p, const typename Plan<T>::C *c);
+template <typename T> int slab_halo_pack(Plan<T> &p, int side, typename Plan<T>::C *buf);
+template <typename T> int slab_halo_add(Plan<T> &p, int side, const typename Plan<T>::C *buf);
+template <typename T> int slab_type1_finish(Plan<T> &p, typename Plan<T>::C *fk_partial);
 
 #define CFB_CUDA_OK(call)                                                              \
     do {                                                                               \

@@ -46,7 +46,8 @@ int stage_fseries(Plan<T> &p)
 {
     T f[3 * MAX_NQUAD] = {0};
     double a[2 * 3 * MAX_NQUAD] = {0};
-    const int nf[3] = {p.nf1, p.nf2, p.nf3};
+    const int nf3 = p.nf3_global();          // slab plans: phihat of the GLOBAL z grid
+    const int nf[3] = {p.nf1, p.nf2, nf3};
     for (int d = 0; d < p.dim; ++d)
         fseries_precomp<T>(nf[d], p.ns, p.es_beta, p.es_c, p.es_halfwidth, f + d * MAX_NQUAD, a + 2 * d * MAX_NQUAD);
     T *d_f = nullptr;
@@ -56,9 +57,9 @@ int stage_fseries(Plan<T> &p)
     CFB_CUDA_OK(cudaMemcpyAsync(d_f, f, sizeof(f), cudaMemcpyHostToDevice, p.stream));
     CFB_CUDA_OK(cudaMemcpyAsync(d_a, a, sizeof(a), cudaMemcpyHostToDevice, p.stream));
     const int q = (int)(2 + 3.0 * (T)(p.ns / 2.0));
-    int nout = std::max(std::max(p.nf1, p.nf2), p.nf3) / 2 + 1;
+    int nout = std::max(std::max(p.nf1, p.nf2), nf3) / 2 + 1;
     dim3 grid((nout + 127) / 128, p.dim);
-    fseries_kernel<T><<<grid, 128, 0, p.stream>>>(p.nf1, p.nf2, p.nf3, q, d_f, d_a, p.fwker[0].template as<T>(),
+    fseries_kernel<T><<<grid, 128, 0, p.stream>>>(p.nf1, p.nf2, nf3, q, d_f, d_a, p.fwker[0].template as<T>(),
                                                   p.fwker[1].template as<T>(), p.fwker[2].template as<T>());
     CFB_CUDA_OK(cudaGetLastError());
     CFB_CUDA_OK(cudaStreamSynchronize(p.stream));   // f/a are stack + temporaries: plan time only

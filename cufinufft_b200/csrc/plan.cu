@@ -78,6 +78,9 @@ static void free_plan(Plan<T> *p)
 {
     if (!p) return;
     if (p->have_fft) cufftDestroy(p->fftplan);
+    if (p->have_fft2d) cufftDestroy(p->fft2d);
+    if (p->have_fftz) cufftDestroy(p->fftz);
+    p->zbuf.release();
     for (DevBuf *b : {&p->recs, &p->keyoff, &p->tilesum, &p->sortidx, &p->idxnupts, &p->binsize, &p->binstartpts, &p->numsubprob,
                       &p->subprobstartpts, &p->subprob_to_bin, &p->scalars, &p->fw, &p->fwker[0], &p->fwker[1],
                       &p->fwker[2], &p->hostside, &p->hcoef})
@@ -91,7 +94,7 @@ static void free_plan(Plan<T> *p)
 // Reference: src/cufinufft.cu:118-175 (+ SETUP_BINSIZE :17-73, spread wrappers' numbins).
 template <typename T>
 static int plan_host_setup(Plan<T> *p, int type, int dim, const int *nmodes, int iflag, int ntransf, T tol,
-                           int maxbatchsize, const cufinufft_opts *user_opts)
+                           int maxbatchsize, const cufinufft_opts *user_opts, int slab_rank = -1, int slab_world = 0)
 {
     if (!nmodes || dim < 1 || dim > 3 || ntransf < 1) return CFB_ERR_BAD_ARG;
     if (type == 3) { fprintf(stderr, "[cufinufft-b200] type 3: Not Implemented yet\n"); return CFB_ERR_NOT_IMPLEMENTED; }
@@ -117,6 +120,21 @@ static int plan_host_setup(Plan<T> *p, int type, int dim, const int *nmodes, int
     p->nf1 = set_nf_type12(p->ms, p->opts.upsampfac, p->ns, m, p->opts.gpu_obinsizex);
     if (dim > 1) p->nf2 = set_nf_type12(p->mt, p->opts.upsampfac, p->ns, m, p->opts.gpu_obinsizey);
     if (dim > 2) p->nf3 = set_nf_type12(p->mu, p->opts.upsampfac, p->ns, m, p->opts.gpu_obinsizez);
+    if (slab_world > 0) {
+        // z-slab share of one 3-D transform (slab.cu): planes [z0, z1) of the global grid + pad halo
+        // planes per side; every slab must be at least one halo thick (single-neighbour exchange)
+        if (dim != 3 || ntransf != 1 || slab_rank < 0 || slab_rank >= slab_world) return CFB_ERR_BAD_ARG;
+        const int pad = (p->ns + 1) / 2;
+        const int base = p->nf3 / slab_world, extra = p->nf3 % slab_world;
+        if (base < pad) { fprintf(stderr, "[cufinufft-b200] slab thinner than the kernel halo\n"); return CFB_ERR_BAD_ARG; }
+        p->slab = true; p->slab_rank = slab_rank; p->slab_world = slab_world;
+        p->nf3g = p->nf3;
+        p->z0 = slab_rank * base + (slab_rank < extra ? slab_rank : extra);
+        p->z1 = p->z0 + base + (slab_rank < extra ? 1 : 0);
+        p->zshift = p->z0 - pad;
+        p->nf3 = p->z1 - p->z0 + 2 * pad;                                          // local planes
+        if ((double)p->nf3g * p->ms * p->mt > 2147483647.0) return CFB_ERR_BAD_ARG;
+    }
     if ((double)p->nf1 * p->nf2 * p->nf3 > 2147483647.0) return CFB_ERR_BAD_ARG;   // int32 cells, as the reference
     p->iflag = iflag >= 0 ? 1 : -1;
     p->ntransf = ntransf;
@@ -144,13 +162,13 @@ static int plan_host_setup(Plan<T> *p, int type, int dim, const int *nmodes, int
 
 template <typename T>
 static int makeplan(int type, int dim, int *nmodes, int iflag, int ntransf, T tol, int maxbatchsize,
-                    Plan<T> **out, cufinufft_opts *user_opts)
+                    Plan<T> **out, cufinufft_opts *user_opts, int slab_rank = -1, int slab_world = 0)
 {
     if (!out) return CFB_ERR_BAD_ARG;
     *out = nullptr;
     Plan<T> *p = new (std::nothrow) Plan<T>();
     if (!p) return CFB_ERR_BAD_ARG;
-    if (int ier = plan_host_setup<T>(p, type, dim, nmodes, iflag, ntransf, tol, maxbatchsize, user_opts)) { delete p; return ier; }
+    if (int ier = plan_host_setup<T>(p, type, dim, nmodes, iflag, ntransf, tol, maxbatchsize, user_opts, slab_rank, slab_world)) { delete p; return ier; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
         fprintf(stderr, "[cufinufft-b200] no CUDA device available: this library has no CPU fallback\n");
@@ -159,7 +177,7 @@ static int makeplan(int type, int dim, int *nmodes, int iflag, int ntransf, T to
     }
     if (p->device < 0 || p->device >= ndev) { delete p; return CFB_ERR_BAD_ARG; }
     DeviceGuard guard(p->device);
-    const int nf[3] = {p->nf1, p->nf2, p->nf3};
+    const int nf[3] = {p->nf1, p->nf2, p->nf3_global()};
 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) { delete p; return CFB_ERR_CUDA; }
@@ -186,13 +204,18 @@ static int makeplan(int type, int dim, int *nmodes, int iflag, int ntransf, T to
         if (p->fw.reserve((size_t)p->maxbatch * p->grid_cells() * sizeof(typename Plan<T>::C))) return fail(CFB_ERR_CUDA);
         for (int d = 0; d < dim; ++d)
             if (p->fwker[d].reserve((size_t)(nf[d] / 2 + 1) * sizeof(T))) return fail(CFB_ERR_CUDA);
-        int n[3];
-        for (int d = 0; d < dim; ++d) n[d] = nf[dim - 1 - d];            // slowest first: {nf3, nf2, nf1}
-        int dist = (int)p->grid_cells();
-        cufftResult fr = cufftPlanMany(&p->fftplan, dim, n, n, 1, dist, n, 1, dist,
-                                       sizeof(T) == 4 ? CUFFT_C2C : CUFFT_Z2Z, p->maxbatch);
-        if (fr != CUFFT_SUCCESS) { fprintf(stderr, "[cufinufft-b200] cufftPlanMany failed (%d)\n", (int)fr); return fail(CFB_ERR_CUFFT); }
-        p->have_fft = true;
+        if (p->slab) {
+            if (p->zbuf.reserve((size_t)p->nf3g * p->mt * p->ms * sizeof(typename Plan<T>::C))) return fail(CFB_ERR_CUDA);
+            if (int e = slab_make_ffts(*p)) { fprintf(stderr, "[cufinufft-b200] slab cufftPlanMany failed\n"); return fail(e); }
+        } else {
+            int n[3];
+            for (int d = 0; d < dim; ++d) n[d] = nf[dim - 1 - d];            // slowest first: {nf3, nf2, nf1}
+            int dist = (int)p->grid_cells();
+            cufftResult fr = cufftPlanMany(&p->fftplan, dim, n, n, 1, dist, n, 1, dist,
+                                           sizeof(T) == 4 ? CUFFT_C2C : CUFFT_Z2Z, p->maxbatch);
+            if (fr != CUFFT_SUCCESS) { fprintf(stderr, "[cufinufft-b200] cufftPlanMany failed (%d)\n", (int)fr); return fail(CFB_ERR_CUFFT); }
+            p->have_fft = true;
+        }
         if (stage_fseries(*p)) return fail(CFB_ERR_CUDA);
     }
     *out = p;
@@ -219,6 +242,7 @@ static int execute(Plan<T> *p, typename Plan<T>::C *c, typename Plan<T>::C *fk)
     using C = typename Plan<T>::C;
     if (!p) return CFB_ERR_BAD_ARG;
     if (p->M < 0) { fprintf(stderr, "[cufinufft-b200] execute before setpts\n"); return CFB_ERR_NO_POINTS_SET; }
+    if (p->slab) { fprintf(stderr, "[cufinufft-b200] slab plans execute through cufinufft*_slab_* (include/cufinufft_b200.h)\n"); return CFB_ERR_BAD_ARG; }
     DeviceGuard guard(p->device);
     cudaStream_t st = p->stream;
     p->launches_exec = 0;
@@ -352,7 +376,7 @@ static int get_reals(Plan<T> *p, int d, T *out)
     DeviceGuard guard(p->device);
     if (d == -1) { out[0] = p->es_beta; out[1] = p->es_c; out[2] = p->es_halfwidth; return 0; }
     if (d < 0 || d >= p->dim || !p->fwker[d].p) return CFB_ERR_BAD_ARG;
-    const int nf[3] = {p->nf1, p->nf2, p->nf3};
+    const int nf[3] = {p->nf1, p->nf2, p->nf3_global()};
     CFB_CUDA_OK(cudaStreamSynchronize(p->stream));
     CFB_CUDA_OK(cudaMemcpy(out, p->fwker[d].p, (size_t)(nf[d] / 2 + 1) * sizeof(T), cudaMemcpyDeviceToHost));
     return 0;
@@ -404,6 +428,32 @@ static int stage_only(Plan<T> *p, typename Plan<T>::C *c, typename Plan<T>::C *f
         return stage_spread(*p, c, fw, nt);
     }
     return stage_interp(*p, c, fw, nt);
+}
+
+// ---- z-slab plans (slab.cu) ----------------------------------------------------
+template <typename T>
+static int slab_info(Plan<T> *p, long long *o)
+{
+    if (!p || !o || !p->slab) return CFB_ERR_BAD_ARG;
+    DeviceGuard guard(p->device);
+    int outside = 0;
+    if (p->M >= 0) {
+        CFB_CUDA_OK(cudaStreamSynchronize(p->stream));
+        CFB_CUDA_OK(cudaMemcpy(&outside, p->scalars.template as<int>() + 3, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    const long long v[12] = {p->z0, p->z1, p->tile_pad, p->nf3, p->nf1, p->nf2, p->nf3g, (long long)p->nf1 * p->nf2,
+                             p->slab_rank, p->slab_world, outside, p->ns};
+    memcpy(o, v, sizeof(v));
+    return 0;
+}
+
+template <typename T, typename F>
+static int slab_call(Plan<T> *p, int want_type, F &&fn)
+{
+    if (!p || !p->slab || (want_type && p->type != want_type)) return CFB_ERR_BAD_ARG;
+    if (p->M < 0) return CFB_ERR_NO_POINTS_SET;
+    DeviceGuard guard(p->device);
+    return fn(*p);
 }
 
 }  // namespace cfb
@@ -524,5 +574,59 @@ int cufinufft_set_interp_engine(cufinufft_plan plan, int e) { if (!PD(plan) || e
 int cufinufftf_set_interp_engine(cufinufftf_plan plan, int e) { if (!PD(plan) || e < 0 || e > 2) return CFB_ERR_BAD_ARG; plan->p->interp_engine = e; return 0; }
 int cufinufft_get_launch_counts(cufinufft_plan plan, int *o) { if (!PD(plan) || !o) return CFB_ERR_BAD_ARG; o[0] = plan->p->launches_setpts; o[1] = plan->p->launches_exec; return 0; }
 int cufinufftf_get_launch_counts(cufinufftf_plan plan, int *o) { if (!PD(plan) || !o) return CFB_ERR_BAD_ARG; o[0] = plan->p->launches_setpts; o[1] = plan->p->launches_exec; return 0; }
+
+// ---- z-slab decomposition (include/cufinufft_b200.h) ----
+int cufinufft_slab_makeplan(int type, int *nmodes, int iflag, double tol, int rank, int world, cufinufft_plan *plan, cufinufft_opts *opts)
+{
+    if (!plan) return CFB_ERR_BAD_ARG;
+    *plan = nullptr;
+    if (world < 1) return CFB_ERR_BAD_ARG;
+    Plan<double> *p = nullptr;
+    int ier = cfb::makeplan<double>(type, 3, nmodes, iflag, 1, tol, 1, &p, opts, rank, world);
+    if (ier) return ier;
+    *plan = new cufinufft_plan_s{p, {}, {}};
+    return 0;
+}
+int cufinufftf_slab_makeplan(int type, int *nmodes, int iflag, float tol, int rank, int world, cufinufftf_plan *plan, cufinufft_opts *opts)
+{
+    if (!plan) return CFB_ERR_BAD_ARG;
+    *plan = nullptr;
+    if (world < 1) return CFB_ERR_BAD_ARG;
+    Plan<float> *p = nullptr;
+    int ier = cfb::makeplan<float>(type, 3, nmodes, iflag, 1, tol, 1, &p, opts, rank, world);
+    if (ier) return ier;
+    *plan = new cufinufftf_plan_s{p, {}, {}};
+    return 0;
+}
+int cufinufft_slab_info(cufinufft_plan plan, long long *out12) { return cfb::slab_info<double>(PD(plan), out12); }
+int cufinufftf_slab_info(cufinufftf_plan plan, long long *out12) { return cfb::slab_info<float>(PD(plan), out12); }
+
+int cufinufft_slab_type2(cuDoubleComplex *c, cuDoubleComplex *fk, cufinufft_plan plan)
+{ return cfb::slab_call<double>(PD(plan), 2, [&](Plan<double> &p) { return cfb::slab_type2<double>(p, reinterpret_cast<double2 *>(c), reinterpret_cast<const double2 *>(fk)); }); }
+int cufinufftf_slab_type2(cuFloatComplex *c, cuFloatComplex *fk, cufinufftf_plan plan)
+{ return cfb::slab_call<float>(PD(plan), 2, [&](Plan<float> &p) { return cfb::slab_type2<float>(p, reinterpret_cast<float2 *>(c), reinterpret_cast<const float2 *>(fk)); }); }
+
+int cufinufft_slab_type1_spread(cuDoubleComplex *c, cufinufft_plan plan)
+{ return cfb::slab_call<double>(PD(plan), 1, [&](Plan<double> &p) { return cfb::slab_type1_spread<double>(p, reinterpret_cast<const double2 *>(c)); }); }
+int cufinufftf_slab_type1_spread(cuFloatComplex *c, cufinufftf_plan plan)
+{ return cfb::slab_call<float>(PD(plan), 1, [&](Plan<float> &p) { return cfb::slab_type1_spread<float>(p, reinterpret_cast<const float2 *>(c)); }); }
+
+int cufinufft_slab_halo_pack(int side, cuDoubleComplex *buf, cufinufft_plan plan)
+{ if (side < 0 || side > 1 || !buf) return CFB_ERR_BAD_ARG;
+  return cfb::slab_call<double>(PD(plan), 0, [&](Plan<double> &p) { return cfb::slab_halo_pack<double>(p, side, reinterpret_cast<double2 *>(buf)); }); }
+int cufinufftf_slab_halo_pack(int side, cuFloatComplex *buf, cufinufftf_plan plan)
+{ if (side < 0 || side > 1 || !buf) return CFB_ERR_BAD_ARG;
+  return cfb::slab_call<float>(PD(plan), 0, [&](Plan<float> &p) { return cfb::slab_halo_pack<float>(p, side, reinterpret_cast<float2 *>(buf)); }); }
+int cufinufft_slab_halo_add(int side, cuDoubleComplex *buf, cufinufft_plan plan)
+{ if (side < 0 || side > 1 || !buf) return CFB_ERR_BAD_ARG;
+  return cfb::slab_call<double>(PD(plan), 0, [&](Plan<double> &p) { return cfb::slab_halo_add<double>(p, side, reinterpret_cast<const double2 *>(buf)); }); }
+int cufinufftf_slab_halo_add(int side, cuFloatComplex *buf, cufinufftf_plan plan)
+{ if (side < 0 || side > 1 || !buf) return CFB_ERR_BAD_ARG;
+  return cfb::slab_call<float>(PD(plan), 0, [&](Plan<float> &p) { return cfb::slab_halo_add<float>(p, side, reinterpret_cast<const float2 *>(buf)); }); }
+
+int cufinufft_slab_type1_finish(cuDoubleComplex *fk_partial, cufinufft_plan plan)
+{ return cfb::slab_call<double>(PD(plan), 1, [&](Plan<double> &p) { return cfb::slab_type1_finish<double>(p, reinterpret_cast<double2 *>(fk_partial)); }); }
+int cufinufftf_slab_type1_finish(cuFloatComplex *fk_partial, cufinufftf_plan plan)
+{ return cfb::slab_call<float>(PD(plan), 1, [&](Plan<float> &p) { return cfb::slab_type1_finish<float>(p, reinterpret_cast<float2 *>(fk_partial)); }); }
 
 }  // extern "C"

@@ -35,7 +35,7 @@ namespace cfb {
 
 template <typename T, int DIM>
 __device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                                         int i, const SortGeo &g, T &xr, T &yr, T &zr)
+                                         int i, const SortGeo &g, T &xr, T &yr, T &zr, int *count_outside = nullptr)
 {
     xr = rescale(x[i], g.nf[0]);
     const int b1 = bin_coord(xr, g.bs[0], g.nb[0]);
@@ -48,10 +48,21 @@ __device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__res
         if (g.nk[1] > 1) cell += g.nk[0] * stencil_cell(yr, g.ns, b2 * g.bs[1], g.nk[1]);
     }
     if (DIM > 2) {
-        zr = rescale(z[i], g.nf[2]);
-        const int b3 = bin_coord(zr, g.bs[2], g.nb[2]);
+        zr = rescale(z[i], g.nfz);
+        // slab plans: bins over the slab-local planes; the record keeps the GLOBAL z_r (weights are
+        // then bit-identical to the undivided transform), the kernels shift the stencil start.
+        // A point outside the slab (caller error) is pulled onto its edge and counted.  The stencil
+        // of a point stays inside the halo for zl in [zlo - 1/2, zhi], so a caller whose own
+        // rescale differs from ours in the last bit at a slab boundary is still served exactly.
+        T zl = zr - (T)g.zshift;
+        if (zl < (T)g.zlo - (T)0.5 || zl > (T)g.zhi) {
+            if (count_outside) atomicAdd(count_outside, 1);
+            zr = zl < (T)g.zlo ? (T)(g.zlo + g.zshift) : (T)(g.zhi + g.zshift);
+            zl = zr - (T)g.zshift;
+        }
+        const int b3 = bin_coord(zl, g.bs[2], g.nb[2]);
         bin += g.nb[0] * g.nb[1] * b3;
-        if (g.nk[2] > 1) cell += g.nk[0] * g.nk[1] * stencil_cell(zr, g.ns, b3 * g.bs[2], g.nk[2]);
+        if (g.nk[2] > 1) cell += g.nk[0] * g.nk[1] * stencil_cell(zl, g.ns, b3 * g.bs[2], g.nk[2]);
     }
     return bin * g.cpb + cell;
 }
@@ -61,14 +72,14 @@ __device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__res
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 key_count_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                 const SortGeo g, int *__restrict__ keycnt, int *__restrict__ rank)
+                 const SortGeo g, int *__restrict__ keycnt, int *__restrict__ rank, int *__restrict__ outside)
 {
     const int lane = threadIdx.x & 31;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
         int i = (int)(base + threadIdx.x);
         bool valid = i < M;
         T xr, yr, zr;
-        int k = valid ? point_key<T, DIM>(x, y, z, i, g, xr, yr, zr) : -1 - lane;
+        int k = valid ? point_key<T, DIM>(x, y, z, i, g, xr, yr, zr, outside) : -1 - lane;
         unsigned peers = __match_any_sync(0xffffffffu, k);
         int leader = __ffs(peers) - 1;
         int rank_in_group = __popc(peers & ((1u << lane) - 1));
@@ -288,13 +299,12 @@ place_points_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, con
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 trivial_order_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                     int nf1, int nf2, int nf3, PtRec<T> *__restrict__ recs)
+                     const SortGeo g, PtRec<T> *__restrict__ recs, int *__restrict__ outside)
 {
     for (long long ii = (long long)blockIdx.x * blockDim.x + threadIdx.x; ii < M; ii += (long long)gridDim.x * blockDim.x) {
         int i = (int)ii;
-        T xr = rescale(x[i], nf1), yr = 0, zr = 0;
-        if (DIM > 1) yr = rescale(y[i], nf2);
-        if (DIM > 2) zr = rescale(z[i], nf3);
+        T xr, yr = 0, zr = 0;
+        point_key<T, DIM>(x, y, z, i, g, xr, yr, zr, outside);      // rescale (+ slab clamp); key unused
         store_rec<T>(recs + i, xr, yr, zr, i);
     }
 }
@@ -328,12 +338,12 @@ static int setpts_dim(Plan<T> &p)
     int blocks = (int)(want < 1 ? 1 : (want > (long long)p.num_sms * 32 ? (long long)p.num_sms * 32 : want));
     p.launches_setpts = 0;
 
+    CFB_CUDA_OK(cudaMemsetAsync(scal, 0, 8 * sizeof(int), st));
     if (!p.sorted) {
         if (M > 0) {
-            trivial_order_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, p.nf1, p.nf2, p.nf3, recs);
+            trivial_order_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, p.sortgeo, recs, p.slab ? scal + 3 : nullptr);
             p.launches_setpts++;
         }
-        CFB_CUDA_OK(cudaMemsetAsync(scal, 0, 8 * sizeof(int), st));
         CFB_CUDA_OK(cudaGetLastError());
         return 0;
     }
@@ -343,7 +353,7 @@ static int setpts_dim(Plan<T> &p)
     const int ntiles = (int)((nscan + SCAN_TILE - 1) / SCAN_TILE);
     CFB_CUDA_OK(cudaMemsetAsync(keyoff, 0, sizeof(int) * (size_t)nscan, st));
     if (M > 0) {
-        key_count_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, g, keyoff, rank);
+        key_count_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, g, keyoff, rank, p.slab ? scal + 3 : nullptr);
         p.launches_setpts++;
     }
     scan_reduce_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nscan, keyoff, tilesum);
@@ -372,6 +382,8 @@ int stage_setpts(Plan<T> &p)
     SortGeo &g = p.sortgeo;
     const int nf[3] = {p.nf1, p.nf2, p.nf3};
     g.ns = p.ns;
+    g.nfz = p.nf3_global(); g.zshift = p.slab ? p.zshift : 0;
+    g.zlo = p.slab ? p.tile_pad : -(1 << 30); g.zhi = p.slab ? p.tile_pad + (p.z1 - p.z0) : (1 << 30);   // ordinary plans: never clamp
     long long cpb = 1;
     for (int d = 0; d < 3; ++d) {
         g.nf[d] = nf[d]; g.bs[d] = p.bs[d]; g.nb[d] = p.nbin[d];

@@ -50,6 +50,7 @@ struct SIArgs {
     int pad, ex, ey, ez;        // tile halo and extents (cells)
     int sy, sz, tile_cells;     // padded tile strides
     int horner, ncoef;
+    int zshift;                 // slab plans: local plane = global plane - zshift (0 otherwise)
     T es_c, es_beta;
     long long fwstride;
 };
@@ -185,6 +186,7 @@ __device__ __forceinline__ void point_weights(const SIArgs<T> &a, const PtRec<T>
                 }
         }
     }
+    if (DIM > 2) zstart -= a.zshift;      // weights from the global coordinate, grid index slab-local
 }
 
 // row weights of all passes for this lane (row-slot r) into w[NACC]
@@ -837,7 +839,7 @@ interp_tile_kernel(const SIArgs<T> a)
                 if (DIM > 2) {
                     const int zs = stencil_start(rec.z, NS);
                     kernel_vector<T, NS, true>(kz, (T)zs - rec.z, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
-                    off += clampi(zs - oz, 0, ez - NS) * ex * ey;
+                    off += clampi(zs - a.zshift - oz, 0, ez - NS) * ex * ey;
                 }
             }
             if (first) {                                  // the tile has landed (weights of the first point overlapped the copy)

@@ -30,6 +30,7 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     a.sy = p.tile_sy; a.sz = p.tile_sz; a.tile_cells = p.tile_cells;
     a.horner = p.opts.gpu_kerevalmeth == 1; a.ncoef = p.horner_ncoef;
     a.es_c = p.es_c; a.es_beta = p.es_beta;
+    a.zshift = p.slab ? p.zshift : 0;
     a.fwstride = (long long)p.grid_cells();
     return a;
 }

@@ -104,6 +104,44 @@ int cufinufftf_set_interp_engine(cufinufftf_plan plan, int engine);
 int cufinufft_get_launch_counts(cufinufft_plan plan, int *out2);
 int cufinufftf_get_launch_counts(cufinufftf_plan plan, int *out2);
 
+/* ---- z-slab decomposition of ONE large 3-D transform over the GPUs of a node ----------------
+ * (BASELINE.json config 5; the reference has no counterpart: its plan lives on one device,
+ * src/cufinufft.cu:101-110, and its 3-D pipeline src/3d/cufinufft3d.cu:15-165 is what is split.)
+ * One process per GPU; rank r of `world` owns the fine-grid planes [z0, z1) with pad = ceil(ns/2)
+ * halo planes per side and the points with floor(z_rescaled) in [z0, z1) (the caller routes the
+ * points: cufinufft_b200/multi.py).  The library does the device work of a rank; the two
+ * exchanges of type 1 are the CALLER's (NCCL send/recv + all-reduce; multi.py uses
+ * torch.distributed) so that libcufinufft.so keeps linking only cudart + cufft.
+ *   slab_makeplan  like makeplan with dim = 3, ntransf = 1; cufinufft*_setpts / _destroy /
+ *                  _set_stream / _set_timing / _get_timing work on the returned plan, execute does not.
+ *   slab_info      out12 = {z0, z1, pad, local planes nz+2pad, nf1, nf2, nf3 (global), nf1*nf2,
+ *                  rank, world, #points of the last setpts that were outside the slab (they are
+ *                  pulled onto its edge: a caller error), ns}
+ *   type 2 (modes -> points), NO communication: `fk` is the full mode array [mu][mt][ms]
+ *                  (replicated on every rank), `c` receives the values at this rank's points.
+ *   type 1 (points -> modes): slab_type1_spread(c); then for side = 0 (low halo, goes to rank-1)
+ *                  and 1 (high halo, goes to rank+1): slab_halo_pack(side, sendbuf) ->
+ *                  [caller sends it to the neighbour] -> on the receiver slab_halo_add(1 - side,
+ *                  recvbuf); then slab_type1_finish(fk_partial): the caller SUMS fk_partial
+ *                  [mu][mt][ms] over the ranks.  Halo buffers hold pad*nf1*nf2 complex numbers.
+ * All pointers are device pointers; work is enqueued on the plan's stream.                     */
+int cufinufft_slab_makeplan(int type, int *nmodes3, int iflag, double tol, int rank, int world,
+                            cufinufft_plan *plan, cufinufft_opts *opts);
+int cufinufftf_slab_makeplan(int type, int *nmodes3, int iflag, float tol, int rank, int world,
+                             cufinufftf_plan *plan, cufinufft_opts *opts);
+int cufinufft_slab_info(cufinufft_plan plan, long long *out12);
+int cufinufftf_slab_info(cufinufftf_plan plan, long long *out12);
+int cufinufft_slab_type2(cuDoubleComplex *c, cuDoubleComplex *fk, cufinufft_plan plan);
+int cufinufftf_slab_type2(cuFloatComplex *c, cuFloatComplex *fk, cufinufftf_plan plan);
+int cufinufft_slab_type1_spread(cuDoubleComplex *c, cufinufft_plan plan);
+int cufinufftf_slab_type1_spread(cuFloatComplex *c, cufinufftf_plan plan);
+int cufinufft_slab_halo_pack(int side, cuDoubleComplex *buf, cufinufft_plan plan);
+int cufinufftf_slab_halo_pack(int side, cuFloatComplex *buf, cufinufftf_plan plan);
+int cufinufft_slab_halo_add(int side, cuDoubleComplex *buf, cufinufft_plan plan);
+int cufinufftf_slab_halo_add(int side, cuFloatComplex *buf, cufinufftf_plan plan);
+int cufinufft_slab_type1_finish(cuDoubleComplex *fk_partial, cufinufft_plan plan);
+int cufinufftf_slab_type1_finish(cuFloatComplex *fk_partial, cufinufftf_plan plan);
+
 #ifdef __cplusplus
 }
 #endif
