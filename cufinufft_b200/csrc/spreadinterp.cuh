@@ -344,21 +344,48 @@ spread_sm_kernel(const SIArgs<T> a)
         int ylo = 1 << 30, yhi = -1, zlo = 1 << 30, zhi = -1;   // touched stencil origins (tile rows), per lane
 
         // add the open run's accumulators into the tile (lanes touch distinct cells)
+        // (the cells of one flush are distinct: all loads are issued before the first store so that
+        // their latencies overlap instead of forming a load -> add -> store chain per pass)
         auto flush_run = [&]() {
             if constexpr (G::MERGE) {
                 __syncwarp();
                 C *cell0 = tile + cur + ix;
+                C v[G::ITERS];
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it) {
+                for (int it = 0; it < G::ITERS; ++it)
+                    if (active && it * G::R + r < G::ROWS) v[it] = cell0[tile_off(it)];
+#pragma unroll
+                for (int it = 0; it < G::ITERS; ++it)
                     if (active && it * G::R + r < G::ROWS) {
-                        C *cell = cell0 + tile_off(it);
-                        C v = *cell;
                         const C d = acc.get(it);
-                        v.x += d.x; v.y += d.y;
-                        *cell = v;
+                        v[it].x += d.x; v[it].y += d.y;
                     }
-                }
+#pragma unroll
+                for (int it = 0; it < G::ITERS; ++it)
+                    if (active && it * G::R + r < G::ROWS) cell0[tile_off(it)] = v[it];
                 acc.zero();
+            }
+        };
+        // one point applied to the tile at once (no run bookkeeping): loads of all passes first
+        auto apply_point = [&](int q) {
+            if constexpr (G::MERGE) {
+                const T *kq = sc.ker + q * G::KP;
+                T wq[G::NACC];
+                load_row_weights<T, DIM, NS>(kq, r, wq);
+                const T k1 = active ? kq[ix] : (T)0;
+                const C cv = sc.c[q];
+                const T cr = cv.x * k1, ci = cv.y * k1;
+                C *cell0 = tile + s_off[q] + ix;
+                C v[G::ITERS];
+#pragma unroll
+                for (int it = 0; it < G::ITERS; ++it)
+                    if (active && it * G::R + r < G::ROWS) v[it] = cell0[tile_off(it)];
+#pragma unroll
+                for (int it = 0; it < G::ITERS; ++it)
+                    if (active && it * G::R + r < G::ROWS) { v[it].x = fma(cr, wq[it], v[it].x); v[it].y = fma(ci, wq[it], v[it].y); }
+#pragma unroll
+                for (int it = 0; it < G::ITERS; ++it)
+                    if (active && it * G::R + r < G::ROWS) cell0[tile_off(it)] = v[it];
             }
         };
 
@@ -387,41 +414,38 @@ spread_sm_kernel(const SIArgs<T> a)
                 int prev = __shfl_up_sync(0xffffffffu, myoff, 1);
                 if (lane == 0) prev = cur;
                 const unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && myoff != prev);
-                if constexpr (G::PREFETCH) {
-                    // operands of point q are fetched one point ahead of their use
-                    T wq[G::NACC];
-                    load_row_weights<T, DIM, NS>(sc.ker, r, wq);
-                    T k1 = active ? sc.ker[ix] : (T)0;
-                    C cv = sc.c[0];
-                    for (int q = 0; q < cnt; ++q) {
-                        T wn[G::NACC];
-                        const int qn = q + 1 < cnt ? q + 1 : q;
-                        const T *kn = sc.ker + qn * G::KP;
-                        load_row_weights<T, DIM, NS>(kn, r, wn);
-                        const T k1n = active ? kn[ix] : (T)0;
-                        const C cvn = sc.c[qn];
-                        if ((starts >> q) & 1u) {
-                            if (cur >= 0) flush_run();
-                            cur = s_off[q];
-                        }
-                        acc.fma(cv.x * k1, cv.y * k1, wq);
-#pragma unroll
-                        for (int j = 0; j < G::NACC; ++j) wq[j] = wn[j];
-                        k1 = k1n; cv = cvn;
-                    }
+                // Short runs (sparse regions): the run bookkeeping + flush costs more than it saves, the
+                // points of this batch go to the tile one by one.  Break-even run length from the
+                // instruction counts of both paths: (8 ITERS + 70) / (2.75 ITERS - 2); single-pass stencils: 8
+                // (below that the load -> add -> store dependence through one cell is cheaper than a flush).
+                constexpr int THR_NUM = G::ITERS > 1 ? 8 * G::ITERS + 70 : 8, THR_DEN = G::ITERS > 1 ? (11 * G::ITERS - 8) / 4 : 1;
+                if (__popc(starts) * THR_NUM > cnt * THR_DEN) {
+                    if (cur >= 0) { flush_run(); cur = -1; }
+                    __syncwarp();
+#pragma unroll 2
+                    for (int q = 0; q < cnt; ++q) apply_point(q);
+                    __syncwarp();
                 } else {
-                    for (int q = 0; q < cnt; ++q) {
+                // run by run: the accumulators live in registers across the tight inner loop (no
+                // branch, no register renaming inside it); a run ends at the next start bit or with the batch
+                int q = 0;
+                while (q < cnt) {
+                    if ((starts >> q) & 1u) {
+                        if (cur >= 0) flush_run();
+                        cur = s_off[q];
+                    }
+                    const unsigned rest = q < 31 ? (starts >> (q + 1)) : 0u;
+                    const int qe = rest ? q + __ffs(rest) : cnt;
+#pragma unroll 2
+                    for (; q < qe; ++q) {
                         const T *kq = sc.ker + q * G::KP;
                         T wq[G::NACC];
                         load_row_weights<T, DIM, NS>(kq, r, wq);
                         const T k1 = active ? kq[ix] : (T)0;
                         const C cv = sc.c[q];
-                        if ((starts >> q) & 1u) {
-                            if (cur >= 0) flush_run();
-                            cur = s_off[q];
-                        }
                         acc.fma(cv.x * k1, cv.y * k1, wq);
                     }
+                }
                 }
             } else {
                 // stencil too large for register accumulators: apply every pass to the tile at once
@@ -462,19 +486,32 @@ spread_sm_kernel(const SIArgs<T> a)
             }
             const int y0 = DIM > 1 ? ylo : 0, ny = DIM > 1 ? yhi - ylo + NS : 1;
             const int z0 = DIM > 2 ? zlo : 0, nz = DIM > 2 ? zhi - zlo + NS : 1;
-            for (int lz = z0; lz < z0 + nz; ++lz) {
-                size_t gz = 0;
-                if (DIM > 2) gz = (size_t)wrap_index(oz + lz, a.nf3) * a.nf1 * a.nf2;
-                for (int ly = y0; ly < y0 + ny; ++ly) {
-                    C *trow = tile + lz * a.sz + ly * a.sy;
-                    size_t gbase = gz;
-                    if (DIM > 1) gbase += (size_t)wrap_index(oy + ly, a.nf2) * a.nf1;
-                    for (int lx = lane; lx < a.ex; lx += 32) {
-                        const C v = trow[lx];
-                        if (v.x != 0 || v.y != 0) {
-                            red_add(fwt + gbase + wrap_index(ox + lx, a.nf1), v.x, v.y);
-                            trow[lx] = C{0, 0};
-                        }
+            // flat index over the touched box [nz][ny][ex]: all lanes busy whatever ex is, four
+            // independent tile loads in flight; (row, x) and (z, y) by exact float reciprocals
+            const int ncell = yhi < 0 && DIM > 1 ? 0 : a.ex * ny * nz;
+            const float inv_ex = 1.0f / (float)a.ex, inv_ny = 1.0f / (float)ny;
+            for (int base = 0; base < ncell; base += 128) {
+                C v[4];
+                C *tp[4];
+                int lx[4], ly[4], lz[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = base + j * 32 + lane;
+                    int row = (int)(((float)idx + 0.5f) * inv_ex);
+                    lx[j] = idx - row * a.ex;
+                    lz[j] = DIM > 2 ? (int)(((float)row + 0.5f) * inv_ny) : 0;
+                    ly[j] = row - lz[j] * ny;
+                    tp[j] = tile + (z0 + lz[j]) * a.sz + (y0 + ly[j]) * a.sy + lx[j];
+                    v[j] = idx < ncell ? *tp[j] : C{0, 0};
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (v[j].x != 0 || v[j].y != 0) {
+                        size_t g = (size_t)wrap_index(ox + lx[j], a.nf1);
+                        if (DIM > 1) g += (size_t)wrap_index(oy + y0 + ly[j], a.nf2) * a.nf1;
+                        if (DIM > 2) g += (size_t)wrap_index(oz + z0 + lz[j], a.nf3) * a.nf1 * a.nf2;
+                        red_add(fwt + g, v[j].x, v[j].y);
+                        *tp[j] = C{0, 0};
                     }
                 }
             }
@@ -561,21 +598,33 @@ spread_gm_kernel(const SIArgs<T> a)
             if (lane == 0) { px = cx; py = cy; pz = cz; }
             const bool differs = mx != px || my != py || mz != pz || (lane == 0 && !open);
             const unsigned starts = G::MERGE ? __ballot_sync(0xffffffffu, lane < cnt && differs) : 0xffffffffu;
-            for (int q = 0; q < cnt; ++q) {
-                const T *kq = sc.ker + q * G::KP;
-                const T k1 = active ? kq[ix] : (T)0;
-                const C cv = sc.c[q];
-                const T cr = cv.x * k1, ci = cv.y * k1;
-                if constexpr (G::MERGE) {
-                    T wq[G::NACC];
-                    load_row_weights<T, DIM, NS>(kq, r, wq);
+            if constexpr (G::MERGE) {
+                int q = 0;
+                while (q < cnt) {
                     if ((starts >> q) & 1u) {
                         if (open) flush_run();
                         cx = sc.x0[q]; cy = sc.y0[q]; cz = sc.z0[q];
                         open = true;
                     }
-                    acc.fma(cr, ci, wq);
-                } else {
+                    const unsigned rest = q < 31 ? (starts >> (q + 1)) : 0u;
+                    const int qe = rest ? q + __ffs(rest) : cnt;
+#pragma unroll 2
+                    for (; q < qe; ++q) {
+                        const T *kq = sc.ker + q * G::KP;
+                        T wq[G::NACC];
+                        load_row_weights<T, DIM, NS>(kq, r, wq);
+                        const T k1 = active ? kq[ix] : (T)0;
+                        const C cv = sc.c[q];
+                        acc.fma(cv.x * k1, cv.y * k1, wq);
+                    }
+                }
+            } else {
+                for (int q = 0; q < cnt; ++q) {
+                    const T *kq = sc.ker + q * G::KP;
+                    const T k1 = active ? kq[ix] : (T)0;
+                    const C cv = sc.c[q];
+                    const T cr = cv.x * k1, ci = cv.y * k1;
+                    {
                     const int gx = wrap_index(sc.x0[q] + ix, a.nf1);
                     const int y0 = sc.y0[q], z0 = sc.z0[q];
 #pragma unroll 4
@@ -589,6 +638,7 @@ spread_gm_kernel(const SIArgs<T> a)
                             if (DIM == 3) o += (size_t)wrap_index(y0 + iy, a.nf2) * a.nf1 + (size_t)wrap_index(z0 + iz, a.nf3) * plane;
                             red_add(fwt + o, cr * wgt, ci * wgt);
                         }
+                    }
                     }
                 }
             }

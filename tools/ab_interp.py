@@ -19,6 +19,12 @@ CASES = [
     dict(name="cfg4-shape type2 2D fp32 ns5 radial x64", modes=(512, 512), M=262_144, tol=1e-4, dtype="float32", dist="radial", ntransf=64),
     dict(name="cfg3-shape type2 3D fp32 ns6 M1e8 blobs", modes=(256, 256, 256), M=100_000_000, tol=1e-5, dtype="float32", dist="blobs"),
     dict(name="cfg5/16 3D fp64 ns10 256^3 M3e7", modes=(256, 256, 256), M=30_000_000, tol=1e-9, dtype="float64", dist="uniform"),
+    # low densities (points per bin << block size): where does the tile engine stop paying?
+    dict(name="3D fp64 ns10 256^3 M8e6 (30 pts/bin)", modes=(256, 256, 256), M=8_000_000, tol=1e-9, dtype="float64", dist="uniform"),
+    dict(name="3D fp64 ns10 256^3 M2e6 (8 pts/bin)", modes=(256, 256, 256), M=2_000_000, tol=1e-9, dtype="float64", dist="uniform"),
+    dict(name="3D fp32 ns6 256^3 M8e6 (30 pts/bin)", modes=(256, 256, 256), M=8_000_000, tol=1e-5, dtype="float32", dist="uniform"),
+    dict(name="2D fp64 ns10 2048^2 M1e6 (61 pts/bin)", modes=(2048, 2048), M=1_000_000, tol=1e-9, dtype="float64", dist="uniform"),
+    dict(name="2D fp32 ns4 1000^2 M2e5 (50 pts/bin)", modes=(1000, 1000), M=200_000, tol=1e-3, dtype="float32", dist="uniform"),
 ]
 
 
