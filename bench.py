@@ -391,6 +391,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--scale", type=float, default=1.0, help="scale M (debug)")
+    ap.add_argument("--opt", action="append", default=[], help="override a cufinufft_opts field, e.g. --opt gpu_binsizex=8 (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -399,6 +400,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = dict(CONFIGS[args.config])
     cfg["M"] = int(cfg["M"] * args.scale)
+    if args.opt:
+        cfg["opts"] = dict(cfg["opts"], **{k: int(v) for k, v in (o.split("=") for o in args.opt)})
+        cfg["name"] += " [" + ",".join(args.opt) + "]"
 
     if args.impl == "reference":
         run_reference_impl(args, cfg, rank)

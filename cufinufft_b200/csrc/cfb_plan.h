@@ -46,6 +46,10 @@ template <> struct alignas(32) PtRec<double> { double x, y, z; long long idx; };
 // geometry of the setpts sort key: bin grid and the stencil-cell grid inside a bin
 struct SortGeo {
     int nf[3], bs[3], nb[3];
+    // internal bins (work items of the tile engines): ibs divides bs, spb = bs / ibs sub-bins per
+    // reference bin and dimension; internal bin = refbin * spbt + sub, so the reference's bin-major
+    // order is kept and its arrays are sums over groups of spbt internal bins
+    int ibs[3], spb[3], spbt;
     int nk[3];      // distinct stencil origins per bin and dimension (1 = key is the bin alone)
     int cpb;        // nk[0]*nk[1]*nk[2]
     int ns;
@@ -73,6 +77,12 @@ struct Plan {
     int nbins = 1;
     int method = 0;                      // effective engine: 1 = GM/GM-sort, 2 = SM tiles
     bool sorted = true;
+    // internal bins: the tile engines' work items may be finer than the reference's bins (smaller
+    // per-warp tiles -> more resident warps); chosen in setpts, ibs == bs when not worth it
+    int ibs[3] = {1, 1, 1};
+    int spb[3] = {1, 1, 1};
+    int nibins = 1;
+    DevBuf isubstart, is2b;              // internal subproblem offsets [nibins+1] and map (unused when ibs == bs)
     // points (borrowed) + derived (owned)
     int M = -1;
     const T *kx = nullptr, *ky = nullptr, *kz = nullptr;
@@ -138,6 +148,7 @@ template <typename T> int stage_interp(Plan<T> &p, typename Plan<T>::C *c, const
 template <typename T> int stage_deconvolve(Plan<T> &p, typename Plan<T>::C *fk, const typename Plan<T>::C *fw, int nt);
 template <typename T> int stage_amplify(Plan<T> &p, const typename Plan<T>::C *fk, typename Plan<T>::C *fw, int nt);
 template <typename T> void plan_tile_geometry(Plan<T> &p);                 // spread.cu
+template <typename T> void choose_internal_bins(Plan<T> &p, long long M);  // spread.cu
 // z-slab stages (slab.cu)
 template <typename T> int slab_make_ffts(Plan<T> &p);
 template <typename T> int slab_type2(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *fk);

@@ -82,7 +82,7 @@ static void free_plan(Plan<T> *p)
     if (p->have_fftz) cufftDestroy(p->fftz);
     p->zbuf.release();
     for (DevBuf *b : {&p->recs, &p->keyoff, &p->tilesum, &p->sortidx, &p->idxnupts, &p->binsize, &p->binstartpts, &p->numsubprob,
-                      &p->subprobstartpts, &p->subprob_to_bin, &p->scalars, &p->fw, &p->fwker[0], &p->fwker[1],
+                      &p->subprobstartpts, &p->subprob_to_bin, &p->isubstart, &p->is2b, &p->scalars, &p->fw, &p->fwker[0], &p->fwker[1],
                       &p->fwker[2], &p->hostside, &p->hcoef})
         b->release();
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
@@ -156,7 +156,9 @@ static int plan_host_setup(Plan<T> *p, int type, int dim, const int *nmodes, int
     for (int d = 0; d < 3; ++d) {
         p->nbin[d] = d < dim ? (int)ceil((T)nf[d] / p->bs[d]) : 1;       // numbins = ceil((FLT)nf/bin), spread2d_wrapper.cu:405-406
         p->nbins *= p->nbin[d];
+        p->ibs[d] = p->bs[d]; p->spb[d] = 1;
     }
+    p->nibins = p->nbins;
     return 0;
 }
 

@@ -33,19 +33,34 @@
 
 namespace cfb {
 
+// reference bin b, sub-bin s inside it and stencil-origin cell inside the sub-bin for one coordinate
+template <typename T>
+__device__ __forceinline__ void dim_key(T xr, int d, const SortGeo &g, int &b, int &s, int &cell)
+{
+    b = bin_coord(xr, g.bs[d], g.nb[d]);
+    int origin = b * g.bs[d];
+    s = 0;
+    if (g.spb[d] > 1) {
+        s = (int)floor((xr - (T)origin) / (T)g.ibs[d]);
+        s = s < 0 ? 0 : (s >= g.spb[d] ? g.spb[d] - 1 : s);
+        origin += s * g.ibs[d];
+    }
+    cell = g.nk[d] > 1 ? stencil_cell(xr, g.ns, origin, g.nk[d]) : 0;
+}
+
+// sort key = ((reference bin * sub-bins per bin + sub-bin) * cells per sub-bin + stencil cell)
 template <typename T, int DIM>
 __device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
                                          int i, const SortGeo &g, T &xr, T &yr, T &zr, int *count_outside = nullptr)
 {
+    int b, sb, c;
     xr = rescale(x[i], g.nf[0]);
-    const int b1 = bin_coord(xr, g.bs[0], g.nb[0]);
-    int bin = b1, cell = 0;
-    if (g.nk[0] > 1) cell = stencil_cell(xr, g.ns, b1 * g.bs[0], g.nk[0]);
+    dim_key(xr, 0, g, b, sb, c);
+    int bin = b, sub = sb, cell = c;
     if (DIM > 1) {
         yr = rescale(y[i], g.nf[1]);
-        const int b2 = bin_coord(yr, g.bs[1], g.nb[1]);
-        bin += g.nb[0] * b2;
-        if (g.nk[1] > 1) cell += g.nk[0] * stencil_cell(yr, g.ns, b2 * g.bs[1], g.nk[1]);
+        dim_key(yr, 1, g, b, sb, c);
+        bin += g.nb[0] * b; sub += g.spb[0] * sb; cell += g.nk[0] * c;
     }
     if (DIM > 2) {
         zr = rescale(z[i], g.nfz);
@@ -60,11 +75,10 @@ __device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__res
             zr = zl < (T)g.zlo ? (T)(g.zlo + g.zshift) : (T)(g.zhi + g.zshift);
             zl = zr - (T)g.zshift;
         }
-        const int b3 = bin_coord(zl, g.bs[2], g.nb[2]);
-        bin += g.nb[0] * g.nb[1] * b3;
-        if (g.nk[2] > 1) cell += g.nk[0] * g.nk[1] * stencil_cell(zl, g.ns, b3 * g.bs[2], g.nk[2]);
+        dim_key(zl, 2, g, b, sb, c);
+        bin += g.nb[0] * g.nb[1] * b; sub += g.spb[0] * g.spb[1] * sb; cell += g.nk[0] * g.nk[1] * c;
     }
-    return bin * g.cpb + cell;
+    return (bin * g.spbt + sub) * g.cpb + cell;
 }
 
 // K1: histogram + rank.  Lanes of a warp that fall on the same key are aggregated into
@@ -247,6 +261,16 @@ scan_bins_kernel(int nbins, int maxsub, const int *__restrict__ binsize, int *__
     if (threadIdx.x == 0) scalars[0] = carry_b;
 }
 
+// internal bins (finer than the reference's): subproblem count per internal bin, to be scanned
+// in place (entry nibins = 0 becomes the total)
+__global__ void __launch_bounds__(256)
+isub_count_kernel(int nibins, int cpb, int maxsub, const int *__restrict__ keyoff, int *__restrict__ isubstart)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nibins) isubstart[b] = (keyoff[(size_t)(b + 1) * cpb] - keyoff[(size_t)b * cpb] + maxsub - 1) / maxsub;
+    else if (b == nibins) isubstart[b] = 0;
+}
+
 // K5: subprob_to_bin[s] = the bin whose slot range contains s (upper bound launch: slots
 // beyond totalnumsubprob exit).  Replaces MapBintoSubProb_* + the blocking D2H/cudaMalloc.
 __global__ void __launch_bounds__(256)
@@ -359,12 +383,25 @@ static int setpts_dim(Plan<T> &p)
     scan_reduce_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nscan, keyoff, tilesum);
     scan_top_kernel<<<1, 1024, 0, st>>>(ntiles, tilesum);
     scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nscan, keyoff, tilesum);
-    bins_from_keys_kernel<<<(p.nbins + 255) / 256, 256, 0, st>>>(p.nbins, g.cpb, keyoff, binsize);
+    bins_from_keys_kernel<<<(p.nbins + 255) / 256, 256, 0, st>>>(p.nbins, g.cpb * g.spbt, keyoff, binsize);
     scan_bins_kernel<<<1, 1024, 0, st>>>(p.nbins, p.opts.gpu_maxsubprobsize, binsize, binstart, nsub, substart, scal);
     p.launches_setpts += 5;
     int maxslots = p.nbins + M / p.opts.gpu_maxsubprobsize + 1;
     map_subprob_kernel<<<(maxslots + 255) / 256, 256, 0, st>>>(p.nbins, maxslots, substart, scal, s2b);
     p.launches_setpts++;
+    if (g.spbt > 1) {
+        // the tile engines' own work list over the internal bins (same construction, finer bins)
+        int *isub = p.isubstart.template as<int>();
+        const long long nis = (long long)p.nibins + 1;
+        const int itiles = (int)((nis + SCAN_TILE - 1) / SCAN_TILE);
+        isub_count_kernel<<<(int)((nis + 255) / 256), 256, 0, st>>>(p.nibins, g.cpb, p.opts.gpu_maxsubprobsize, keyoff, isub);
+        scan_reduce_kernel<<<itiles, SCAN_THREADS, 0, st>>>(nis, isub, tilesum);
+        scan_top_kernel<<<1, 1024, 0, st>>>(itiles, tilesum);
+        scan_apply_kernel<<<itiles, SCAN_THREADS, 0, st>>>(nis, isub, tilesum);
+        int islots = p.nibins + M / p.opts.gpu_maxsubprobsize + 1;
+        map_subprob_kernel<<<(islots + 255) / 256, 256, 0, st>>>(p.nibins, islots, isub, isub + p.nibins, p.is2b.template as<int>());
+        p.launches_setpts += 5;
+    }
     if (M > 0) {
         place_points_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, g, keyoff, rank, recs);
         p.launches_setpts++;
@@ -381,20 +418,23 @@ int stage_setpts(Plan<T> &p)
     // point set, else the bin alone
     SortGeo &g = p.sortgeo;
     const int nf[3] = {p.nf1, p.nf2, p.nf3};
+    choose_internal_bins(p, (long long)p.M);        // p.ibs / p.spb / p.nibins + the tile geometry that goes with them
     g.ns = p.ns;
     g.nfz = p.nf3_global(); g.zshift = p.slab ? p.zshift : 0;
     g.zlo = p.slab ? p.tile_pad : -(1 << 30); g.zhi = p.slab ? p.tile_pad + (p.z1 - p.z0) : (1 << 30);   // ordinary plans: never clamp
     long long cpb = 1;
     for (int d = 0; d < 3; ++d) {
         g.nf[d] = nf[d]; g.bs[d] = p.bs[d]; g.nb[d] = p.nbin[d];
-        g.nk[d] = d < p.dim ? p.bs[d] + (p.ns & 1) : 1;
+        g.ibs[d] = p.ibs[d]; g.spb[d] = p.spb[d];
+        g.nk[d] = d < p.dim ? p.ibs[d] + (p.ns & 1) : 1;
         cpb *= g.nk[d];
     }
-    long long nkeys = cpb * p.nbins;
+    g.spbt = p.spb[0] * p.spb[1] * p.spb[2];
+    long long nkeys = cpb * p.nibins;
     if (!p.fine_sort_allowed || nkeys > 8LL * (long long)M + (1LL << 22) || nkeys > 2000000000LL) {
         g.nk[0] = g.nk[1] = g.nk[2] = 1;
         cpb = 1;
-        nkeys = p.nbins;
+        nkeys = p.nibins;
     }
     g.cpb = (int)cpb;
     CFB_CUDA_OK(p.recs.reserve(M * sizeof(PtRec<T>)));
@@ -405,6 +445,10 @@ int stage_setpts(Plan<T> &p)
     }
     size_t maxslots = (size_t)p.nbins + M / (size_t)p.opts.gpu_maxsubprobsize + 1;
     CFB_CUDA_OK(p.subprob_to_bin.reserve(maxslots * sizeof(int)));
+    if (g.spbt > 1) {
+        CFB_CUDA_OK(p.isubstart.reserve(((size_t)p.nibins + 1 + 4) * sizeof(int)));
+        CFB_CUDA_OK(p.is2b.reserve(((size_t)p.nibins + M / (size_t)p.opts.gpu_maxsubprobsize + 1) * sizeof(int)));
+    }
     p.idx_valid = false;
     switch (p.dim) {
         case 1: return setpts_dim<T, 1>(p);

@@ -60,9 +60,9 @@ void plan_tile_geometry(Plan<T> &p)
 {
     const int cell = (int)sizeof(typename Plan<T>::C);
     p.tile_pad = (p.ns + 1) / 2;
-    const int ex = p.bs[0] + 2 * p.tile_pad;
-    const int ey = p.dim > 1 ? p.bs[1] + 2 * p.tile_pad : 1;
-    const int ez = p.dim > 2 ? p.bs[2] + 2 * p.tile_pad : 1;
+    const int ex = p.ibs[0] + 2 * p.tile_pad;
+    const int ey = p.dim > 1 ? p.ibs[1] + 2 * p.tile_pad : 1;
+    const int ez = p.dim > 2 ? p.ibs[2] + 2 * p.tile_pad : 1;
     long long best_score = -1;
     int best_sy = ex, best_rows = ey;
     const long long base_cells = (long long)ex * ey * ez;
@@ -96,11 +96,47 @@ void plan_tile_geometry(Plan<T> &p)
     p.sm_warps = (int)w;
 }
 
+// Internal bins for the SM spread engine.  The reference's bins (16x16x2 in 3-D, 32x32 in 2-D) give
+// every warp a private tile of 20-40 KB, i.e. 5-12 resident warps per SM, and the kernel is then
+// bound by the dependent-issue rate of those few warps (profiles/r01k: 30 % issue slots used, stall
+// reason "wait").  Splitting each reference bin into sub-bins shrinks the tile and multiplies the
+// resident warps; the halo (flush) overhead per point grows, so the split stops at ~14 KB per warp
+// (16 warps per SM) and needs >= 64 points per sub-bin on average.  Reference-facing arrays are
+// unaffected: the sort stays bin-major and their values are sums over the sub-bins (setpts.cu).
+template <typename T>
+void choose_internal_bins(Plan<T> &p, long long M)
+{
+    for (int d = 0; d < 3; ++d) { p.ibs[d] = p.bs[d]; p.spb[d] = 1; }
+    p.nibins = p.nbins;
+    plan_tile_geometry(p);
+    if (!(p.type == 1 && p.method == 2 && p.sorted) || p.dim == 1) return;
+    const size_t target = 14 * 1024;
+    for (;;) {
+        size_t per_warp;
+        switch (p.dim) {
+            case 2: per_warp = sm_spread_smem_per_warp<T, 2>(p.ns, p.tile_cells); break;
+            default: per_warp = sm_spread_smem_per_warp<T, 3>(p.ns, p.tile_cells); break;
+        }
+        if (p.sm_warps > 0 && per_warp <= target) break;
+        // halve the longest halvable dimension (even, >= 8 cells, >= the kernel width afterwards)
+        int best = -1;
+        for (int d = 0; d < p.dim; ++d)
+            if (p.ibs[d] % 2 == 0 && p.ibs[d] >= 8 && p.ibs[d] / 2 >= (p.ns + 1) / 2 && (best < 0 || p.ibs[d] > p.ibs[best])) best = d;
+        if (best < 0) break;
+        const long long nib = (long long)p.nibins * 2;
+        if (M < 64 * nib || nib > (1LL << 28)) break;
+        p.ibs[best] /= 2; p.spb[best] *= 2; p.nibins = (int)nib;
+        plan_tile_geometry(p);
+    }
+}
+
 template int stage_spread<float>(Plan<float> &, const float2 *, float2 *, int);
 template int stage_spread<double>(Plan<double> &, const double2 *, double2 *, int);
 template int stage_interp<float>(Plan<float> &, float2 *, const float2 *, int);
 template int stage_interp<double>(Plan<double> &, double2 *, const double2 *, int);
 template void plan_tile_geometry<float>(Plan<float> &);
 template void plan_tile_geometry<double>(Plan<double> &);
+template void choose_internal_bins<float>(Plan<float> &, long long);
+template void choose_internal_bins<double>(Plan<double> &, long long);
 
 }  // namespace cfb

@@ -41,8 +41,14 @@ struct SIArgs {
     const PtRec<T> *recs;       // sorted point records
     C *c;                       // strengths in (spread) / values out (interp), [nt][M]
     C *fw;                      // fine grids [nt][nf3][nf2][nf1]
-    const int *binstart, *binsize, *s2b, *substart, *scalars;
+    // work list of the tile engines over the INTERNAL bins (== the reference's bins unless setpts
+    // split them): keyoff[ib * cpb] = first sorted point of internal bin ib, s2b / substart = the
+    // subproblem -> bin map and offsets, *nsub = number of subproblems
+    const int *keyoff, *s2b, *substart, *nsub;
     int *counter;               // global work counter (zeroed before launch)
+    int cpb;                    // sort keys per internal bin
+    int rbs1, rbs2, rbs3;       // reference bin size; bs1..3 below are the internal (tile) bin size
+    int spb1, spb2, spbt;       // sub-bins per reference bin: x, y, total
     const T *hcoef;             // Horner coefficients [ncoef][NS] as T (device)
     int M, nt, maxsub;
     int nf1, nf2, nf3;
@@ -274,6 +280,25 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 template <typename T>
 __device__ __forceinline__ PtRec<T> null_rec() { PtRec<T> r; r.x = 0; r.y = 0; r.z = 0; r.idx = 0; return r; }
 
+// Work item s (one subproblem: <= maxsub consecutive sorted points of one internal bin) ->
+// its point range and the origin of its tile (bin origin minus the halo).
+template <typename T, int DIM>
+__device__ __forceinline__ void decode_subproblem(const SIArgs<T> &a, int s, int &pstart, int &n, int &ox, int &oy, int &oz)
+{
+    const int bin = a.s2b[s];
+    const int k = s - a.substart[bin];
+    const int p0 = a.keyoff[(size_t)bin * a.cpb], p1 = a.keyoff[(size_t)(bin + 1) * a.cpb];
+    pstart = p0 + k * a.maxsub;
+    n = min(a.maxsub, p1 - pstart);
+    const int rb = bin / a.spbt, sub = bin - rb * a.spbt;
+    const int b1 = rb % a.nb1, b23 = rb / a.nb1;
+    const int s1 = sub % a.spb1, s23 = sub / a.spb1;
+    ox = b1 * a.rbs1 + s1 * a.bs1 - a.pad;
+    oy = 0; oz = 0;
+    if (DIM > 1) { const int b2 = b23 % a.nb2, s2 = s23 % a.spb2; oy = b2 * a.rbs2 + s2 * a.bs2 - a.pad; }
+    if (DIM > 2) { const int b3 = b23 / a.nb2, s3 = s23 / a.spb2; oz = b3 * a.rbs3 + s3 * a.bs3 - a.pad; }
+}
+
 // =============================================================================
 // SM spread: warp-private tile, run accumulation in registers, lane-per-cell flushes.
 // dynamic smem: [hcoef 18*16 T][per warp: tile C[tile_cells] | scratch]
@@ -296,7 +321,7 @@ spread_sm_kernel(const SIArgs<T> a)
 
     const bool active = lane < G::LANES;
     const int r = active ? lane / NS : 0, ix = active ? lane - r * NS : 0;
-    const int nsub = a.scalars[0];
+    const int nsub = *a.nsub;
     const long long total = (long long)nsub * a.nt;
 
     int toff[G::TOFF_REGS ? G::ITERS : 1];
@@ -327,13 +352,8 @@ spread_sm_kernel(const SIArgs<T> a)
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= total) break;
         const int t = (int)(w / nsub), s = (int)(w - (long long)t * nsub);
-        const int bin = a.s2b[s];
-        const int k = s - a.substart[bin];
-        const int pstart = a.binstart[bin] + k * a.maxsub;
-        const int n = min(a.maxsub, a.binsize[bin] - k * a.maxsub);
-        int b1 = bin % a.nb1, b23 = bin / a.nb1;
-        int b2 = DIM > 1 ? b23 % a.nb2 : 0, b3 = DIM > 2 ? b23 / a.nb2 : 0;
-        const int ox = b1 * a.bs1 - a.pad, oy = b2 * a.bs2 - a.pad, oz = b3 * a.bs3 - a.pad;
+        int pstart, n, ox, oy, oz;
+        decode_subproblem<T, DIM>(a, s, pstart, n, ox, oy, oz);
         const C *cin = a.c + (size_t)t * a.M;
         C *fwt = a.fw + (size_t)t * a.fwstride;
         const PtRec<T> *recs = a.recs + pstart;
@@ -828,7 +848,7 @@ interp_tile_kernel(const SIArgs<T> a)
     __shared__ long long s_work;
     stage_horner<T, NS>(a, s_hc);
 
-    const int nsub = a.scalars[0];
+    const int nsub = *a.nsub;
     const long long total = (long long)nsub * a.nt;
     const int ex = a.ex, ey = a.ey, ez = a.ez;
     const int rows = ey * ez;
@@ -842,13 +862,8 @@ interp_tile_kernel(const SIArgs<T> a)
         const long long w = s_work;
         if (w >= total) break;
         const int t = (int)(w / nsub), s = (int)(w - (long long)t * nsub);
-        const int bin = a.s2b[s];
-        const int k = s - a.substart[bin];
-        const int pstart = a.binstart[bin] + k * a.maxsub;
-        const int n = min(a.maxsub, a.binsize[bin] - k * a.maxsub);
-        const int b1 = bin % a.nb1, b23 = bin / a.nb1;
-        const int b2 = DIM > 1 ? b23 % a.nb2 : 0, b3 = DIM > 2 ? b23 / a.nb2 : 0;
-        const int ox = b1 * a.bs1 - a.pad, oy = b2 * a.bs2 - a.pad, oz = b3 * a.bs3 - a.pad;
+        int pstart, n, ox, oy, oz;
+        decode_subproblem<T, DIM>(a, s, pstart, n, ox, oy, oz);
         C *cout = a.c + (size_t)t * a.M;
         const C *fwt = a.fw + (size_t)t * a.fwstride;
         const PtRec<T> *recs = a.recs + pstart;

@@ -17,16 +17,21 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     SIArgs<T> a;
     a.recs = p.recs.template as<PtRec<T>>();
     a.c = nullptr; a.fw = nullptr;
-    a.binstart = p.binstartpts.template as<int>(); a.binsize = p.binsize.template as<int>();
-    a.s2b = p.subprob_to_bin.template as<int>(); a.substart = p.subprobstartpts.template as<int>();
-    a.scalars = p.scalars.template as<int>(); a.counter = p.scalars.template as<int>() + 1;
+    const bool split = p.nibins != p.nbins;             // internal bins finer than the reference's (setpts.cu)
+    a.keyoff = p.keyoff.template as<int>(); a.cpb = p.sortgeo.cpb;
+    a.s2b = split ? p.is2b.template as<int>() : p.subprob_to_bin.template as<int>();
+    a.substart = split ? p.isubstart.template as<int>() : p.subprobstartpts.template as<int>();
+    a.nsub = split ? p.isubstart.template as<int>() + p.nibins : p.scalars.template as<int>();
+    a.counter = p.scalars.template as<int>() + 1;
     a.hcoef = p.hcoef.template as<T>();
     a.M = p.M; a.nt = nt; a.maxsub = p.opts.gpu_maxsubprobsize;
     a.nf1 = p.nf1; a.nf2 = p.nf2; a.nf3 = p.nf3;
-    a.bs1 = p.bs[0]; a.bs2 = p.bs[1]; a.bs3 = p.bs[2]; a.nb1 = p.nbin[0]; a.nb2 = p.nbin[1];
+    a.bs1 = p.ibs[0]; a.bs2 = p.ibs[1]; a.bs3 = p.ibs[2]; a.nb1 = p.nbin[0]; a.nb2 = p.nbin[1];
+    a.rbs1 = p.bs[0]; a.rbs2 = p.bs[1]; a.rbs3 = p.bs[2];
+    a.spb1 = p.spb[0]; a.spb2 = p.spb[1]; a.spbt = p.spb[0] * p.spb[1] * p.spb[2];
     a.pad = p.tile_pad;
-    a.ex = p.bs[0] + 2 * p.tile_pad; a.ey = p.dim > 1 ? p.bs[1] + 2 * p.tile_pad : 1;
-    a.ez = p.dim > 2 ? p.bs[2] + 2 * p.tile_pad : 1;
+    a.ex = p.ibs[0] + 2 * p.tile_pad; a.ey = p.dim > 1 ? p.ibs[1] + 2 * p.tile_pad : 1;
+    a.ez = p.dim > 2 ? p.ibs[2] + 2 * p.tile_pad : 1;
     a.sy = p.tile_sy; a.sz = p.tile_sz; a.tile_cells = p.tile_cells;
     a.horner = p.opts.gpu_kerevalmeth == 1; a.ncoef = p.horner_ncoef;
     a.es_c = p.es_c; a.es_beta = p.es_beta;
@@ -76,6 +81,10 @@ static int do_interp_tile(Plan<T> &p, SIArgs<T> &a, bool &done)
     const size_t cells = (size_t)a.ex * a.ey * a.ez;
     const size_t smem = head + cells * sizeof(C);
     if (smem + 1024 > (size_t)p.max_smem_optin) return 0;
+    // Sparse inputs: a tile of `cells` grid values is staged for every subproblem, which only pays
+    // when enough points share it.  Measured crossover (tools/ab_interp.py, profiles/r01j_ab_lowdensity):
+    // about one point per 64 tile cells (3-D fp64 ns=10: 127 points per bin, 2-D fp32 ns=4: 20).
+    if (p.interp_engine == 0 && (unsigned long long)p.M * 64ull < (unsigned long long)p.nbins * cells) return 0;
     const int threads = smem > 96 * 1024 ? 512 : 256;
     CFB_CUDA_OK(cudaFuncSetAttribute(interp_tile_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
