@@ -372,7 +372,7 @@ static int setpts_dim(Plan<T> &p)
         return 0;
     }
     const SortGeo g = p.sortgeo;
-    const long long nkeys = (long long)p.nbins * g.cpb;
+    const long long nkeys = (long long)p.nibins * g.cpb;
     const long long nscan = nkeys + 1;                       // trailing total
     const int ntiles = (int)((nscan + SCAN_TILE - 1) / SCAN_TILE);
     CFB_CUDA_OK(cudaMemsetAsync(keyoff, 0, sizeof(int) * (size_t)nscan, st));
