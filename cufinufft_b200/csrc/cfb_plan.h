@@ -109,6 +109,7 @@ struct Plan {
     int tile_pad = 0;                    // ceil(ns/2)
     int tile_sy = 0, tile_sz = 0;        // padded strides (cells)
     int tile_cells = 0;
+    int tile_cost = 0;                   // shared-memory wavefronts per point of the chosen tile layout (bank-conflict model)
     int sm_warps = 0;                    // warps per block for the SM spread kernel (0 = SM unusable)
     int interp_engine = 0;               // 0 auto (tile when sorted and it fits), 1 gather, 2 tile
     // z-slab decomposition of one 3-D transform (slab.cu): this plan owns the fine-grid

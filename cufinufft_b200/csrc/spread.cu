@@ -64,7 +64,7 @@ void plan_tile_geometry(Plan<T> &p)
     const int ey = p.dim > 1 ? p.ibs[1] + 2 * p.tile_pad : 1;
     const int ez = p.dim > 2 ? p.ibs[2] + 2 * p.tile_pad : 1;
     long long best_score = -1;
-    int best_sy = ex, best_rows = ey;
+    int best_sy = ex, best_rows = ey, best_cost = 0;
     const long long base_cells = (long long)ex * ey * ez;
     for (int sy = ex; sy < ex + 16; ++sy) {
         for (int rows = ey; rows < ey + (p.dim > 2 ? 16 : 1); ++rows) {
@@ -72,11 +72,12 @@ void plan_tile_geometry(Plan<T> &p)
             if (cells * 10 > base_cells * 13 && !(sy == ex && rows == ey)) continue;   // <= 30 % padding
             int cost = layout_cost(p.dim, p.ns, sy, sy * rows, cell);
             long long score = (long long)cost * 1000000 + cells;
-            if (best_score < 0 || score < best_score) { best_score = score; best_sy = sy; best_rows = rows; }
+            if (best_score < 0 || score < best_score) { best_score = score; best_sy = sy; best_rows = rows; best_cost = cost; }
         }
         if (p.dim == 1) break;
     }
     if (p.dim == 1) { best_sy = ex; best_rows = 1; }
+    p.tile_cost = best_cost;
     p.tile_sy = p.dim == 1 ? ((ex + 1) & ~1) : best_sy;
     p.tile_sz = p.tile_sy * best_rows;
     long long cells = p.dim == 1 ? p.tile_sy : (p.dim == 2 ? (long long)p.tile_sy * ey : (long long)p.tile_sz * ez);
@@ -118,13 +119,22 @@ void choose_internal_bins(Plan<T> &p, long long M)
             default: per_warp = sm_spread_smem_per_warp<T, 3>(p.ns, p.tile_cells); break;
         }
         if (p.sm_warps > 0 && per_warp <= target) break;
-        // halve the longest halvable dimension (even, >= 8 cells, >= the kernel width afterwards)
-        int best = -1;
-        for (int d = 0; d < p.dim; ++d)
-            if (p.ibs[d] % 2 == 0 && p.ibs[d] >= 8 && p.ibs[d] / 2 >= (p.ns + 1) / 2 && (best < 0 || p.ibs[d] > p.ibs[best])) best = d;
-        if (best < 0) break;
+        // halve one dimension (even, >= 8 cells): the one whose halved tile has the cheapest
+        // bank-conflict-free layout, then the fewest cells (in 3-D that keeps x = 16 + halo = 22
+        // cells, whose natural stride is conflict free for ns = 6, and halves y)
         const long long nib = (long long)p.nibins * 2;
         if (M < 64 * nib || nib > (1LL << 28)) break;
+        int best = -1;
+        long long best_score = 0;
+        for (int d = 0; d < p.dim; ++d) {
+            if (p.ibs[d] % 2 != 0 || p.ibs[d] < 8) continue;
+            p.ibs[d] /= 2;
+            plan_tile_geometry(p);
+            const long long score = (long long)p.tile_cost * (1LL << 32) + p.tile_cells;
+            p.ibs[d] *= 2;
+            if (best < 0 || score < best_score) { best = d; best_score = score; }
+        }
+        if (best < 0) { plan_tile_geometry(p); break; }
         p.ibs[best] /= 2; p.spb[best] *= 2; p.nibins = (int)nib;
         plan_tile_geometry(p);
     }

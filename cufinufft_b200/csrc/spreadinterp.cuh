@@ -96,10 +96,11 @@ inline int sm_spread_max_warps(int dim, int ns, int real_bytes)
 }
 
 // bytes of per-warp scratch: ker[32*KP] T | c[32] C | x0,y0,z0[32] int | red[8*33] C (interp only uses it)
-template <typename T, int DIM, int NS>
+template <typename T, int DIM, int NS, bool WITH_RED = true>
 __host__ __device__ constexpr size_t warp_scratch_bytes()
 {
-    return (size_t)32 * Geo<T, DIM, NS>::KP * sizeof(T) + 32 * 2 * sizeof(T) + 3 * 32 * sizeof(int) + 8 * 34 * 2 * sizeof(T);
+    return (size_t)32 * Geo<T, DIM, NS>::KP * sizeof(T) + 32 * 2 * sizeof(T) + 3 * 32 * sizeof(int) +
+           (WITH_RED ? 8 * 34 * 2 * sizeof(T) : 0);      // the spread kernels do not carry the reduction buffer
 }
 
 template <typename T, int DIM, int NS>
@@ -303,16 +304,18 @@ __device__ __forceinline__ void decode_subproblem(const SIArgs<T> &a, int s, int
 // SM spread: warp-private tile, run accumulation in registers, lane-per-cell flushes.
 // dynamic smem: [hcoef 18*16 T][per warp: tile C[tile_cells] | scratch]
 // =============================================================================
-template <typename T, int DIM, int NS>
+template <typename T, int DIM, int NS, bool HORNER>
 __global__ void __launch_bounds__(32 * Geo<T, DIM, NS>::SM_MAXW)
-spread_sm_kernel(const SIArgs<T> a)
+spread_sm_kernel(const SIArgs<T> a_in)
 {
+    SIArgs<T> a = a_in;
+    a.horner = HORNER ? 1 : 0;          // compile-time constant: the other evaluator's code is not emitted
     using C = typename cplx_of<T>::type;
     using G = Geo<T, DIM, NS>;
     extern __shared__ __align__(16) unsigned char smem[];
     T *s_hc = reinterpret_cast<T *>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t per_warp = (size_t)a.tile_cells * sizeof(C) + warp_scratch_bytes<T, DIM, NS>();
+    const size_t per_warp = (size_t)a.tile_cells * sizeof(C) + warp_scratch_bytes<T, DIM, NS, false>();
     unsigned char *wbase = smem + 18 * 16 * sizeof(T) + warp * per_warp;
     C *tile = reinterpret_cast<C *>(wbase);
     Scratch<T, DIM, NS> sc(wbase + (size_t)a.tile_cells * sizeof(C));
@@ -544,10 +547,12 @@ spread_sm_kernel(const SIArgs<T> a)
 // GM / GM-sort spread: same lane-per-cell mapping and run accumulation, runs go straight
 // into the fine grid with vector RED (no tile).  Work unit = 256 consecutive points.
 // =============================================================================
-template <typename T, int DIM, int NS>
+template <typename T, int DIM, int NS, bool HORNER>
 __global__ void __launch_bounds__(256)
-spread_gm_kernel(const SIArgs<T> a)
+spread_gm_kernel(const SIArgs<T> a_in)
 {
+    SIArgs<T> a = a_in;
+    a.horner = HORNER ? 1 : 0;          // compile-time constant: the other evaluator's code is not emitted
     using C = typename cplx_of<T>::type;
     using G = Geo<T, DIM, NS>;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -677,10 +682,12 @@ spread_gm_kernel(const SIArgs<T> a)
 // the per-lane partial sums of 8 points are parked in shared memory [point][lane] and summed by
 // lane = (point, quarter) with two shuffle steps.  Result scattered to c[index].
 // =============================================================================
-template <typename T, int DIM, int NS>
+template <typename T, int DIM, int NS, bool HORNER>
 __global__ void __launch_bounds__(256)
-interp_kernel(const SIArgs<T> a)
+interp_kernel(const SIArgs<T> a_in)
 {
+    SIArgs<T> a = a_in;
+    a.horner = HORNER ? 1 : 0;          // compile-time constant: the other evaluator's code is not emitted
     using C = typename cplx_of<T>::type;
     using G = Geo<T, DIM, NS>;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -837,10 +844,14 @@ template <typename T, int DIM, int NS> struct TileInterp {
     static constexpr bool ROLL_Z = DIM == 3 && NS >= 8;      // plane loop rolled (kz indexed dynamically)
 };
 
-template <typename T, int DIM, int NS>
-__global__ void __launch_bounds__(512)
-interp_tile_kernel(const SIArgs<T> a)
+// 1-D / 2-D: 256 threads, registers capped for three blocks per SM (the fp64 kernels are bound by the
+// FP64 pipe and the shared-memory read path: more resident warps keep both busier); 3-D: up to 512.
+template <typename T, int DIM, int NS, bool HORNER>
+__global__ void __launch_bounds__(DIM == 3 ? 512 : 256, DIM == 3 ? 1 : 3)
+interp_tile_kernel(const SIArgs<T> a_in)
 {
+    SIArgs<T> a = a_in;
+    a.horner = HORNER ? 1 : 0;          // compile-time constant: the other evaluator's code is not emitted
     using C = typename cplx_of<T>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     T *s_hc = reinterpret_cast<T *>(smem);

@@ -40,28 +40,28 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     return a;
 }
 
-template <typename T, int DIM, int NS>
-static int do_spread(Plan<T> &p, SIArgs<T> &a)
+template <typename T, int DIM, int NS, bool HORNER>
+static int do_spread_h(Plan<T> &p, SIArgs<T> &a)
 {
     using C = typename Plan<T>::C;
     const size_t head = 18 * 16 * sizeof(T);
     if (p.method == 2 && p.sm_warps > 0) {
-        size_t per_warp = (size_t)p.tile_cells * sizeof(C) + warp_scratch_bytes<T, DIM, NS>();
+        size_t per_warp = (size_t)p.tile_cells * sizeof(C) + warp_scratch_bytes<T, DIM, NS, false>();
         size_t smem = head + (size_t)p.sm_warps * per_warp;
-        CFB_CUDA_OK(cudaFuncSetAttribute(spread_sm_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CFB_CUDA_OK(cudaFuncSetAttribute(spread_sm_kernel<T, DIM, NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int blocks_per_sm = (int)((size_t)p.max_smem_optin / (smem + 1024));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         if (blocks_per_sm * p.sm_warps > 32) blocks_per_sm = 32 / p.sm_warps > 0 ? 32 / p.sm_warps : 1;
         CFB_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(int), p.stream));
-        spread_sm_kernel<T, DIM, NS><<<p.num_sms * blocks_per_sm, 32 * p.sm_warps, smem, p.stream>>>(a);
+        spread_sm_kernel<T, DIM, NS, HORNER><<<p.num_sms * blocks_per_sm, 32 * p.sm_warps, smem, p.stream>>>(a);
     } else {
         const int warps = 8;
         size_t smem = head + warps * warp_scratch_bytes<T, DIM, NS>();
-        CFB_CUDA_OK(cudaFuncSetAttribute(spread_gm_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CFB_CUDA_OK(cudaFuncSetAttribute(spread_gm_kernel<T, DIM, NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         long long nb = (((long long)p.M + 255) / 256 * a.nt + warps - 1) / warps;
         long long cap = (long long)p.num_sms * 8;
         int blocks = (int)(nb < 1 ? 1 : (nb > cap ? cap : nb));
-        spread_gm_kernel<T, DIM, NS><<<blocks, 32 * warps, smem, p.stream>>>(a);
+        spread_gm_kernel<T, DIM, NS, HORNER><<<blocks, 32 * warps, smem, p.stream>>>(a);
     }
     p.launches_exec++;
     CFB_CUDA_OK(cudaGetLastError());
@@ -71,7 +71,7 @@ static int do_spread(Plan<T> &p, SIArgs<T> &a)
 // Tile engine (interp_tile_kernel): used whenever the points are bin-sorted and the bin tile
 // with its halo fits in shared memory; the gather engine (interp_kernel) serves the rest
 // (gpu_sort = 0, very wide 3-D fp64 stencils).  p.interp_engine: 0 auto, 1 gather, 2 tile.
-template <typename T, int DIM, int NS>
+template <typename T, int DIM, int NS, bool HORNER>
 static int do_interp_tile(Plan<T> &p, SIArgs<T> &a, bool &done)
 {
     using C = typename Plan<T>::C;
@@ -85,36 +85,48 @@ static int do_interp_tile(Plan<T> &p, SIArgs<T> &a, bool &done)
     // when enough points share it.  Measured crossover (tools/ab_interp.py, profiles/r01j_ab_lowdensity):
     // about one point per 64 tile cells (3-D fp64 ns=10: 127 points per bin, 2-D fp32 ns=4: 20).
     if (p.interp_engine == 0 && (unsigned long long)p.M * 64ull < (unsigned long long)p.nbins * cells) return 0;
-    const int threads = smem > 96 * 1024 ? 512 : 256;
-    CFB_CUDA_OK(cudaFuncSetAttribute(interp_tile_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = (DIM == 3 && smem > 96 * 1024) ? 512 : 256;
+    CFB_CUDA_OK(cudaFuncSetAttribute(interp_tile_kernel<T, DIM, NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CFB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, interp_tile_kernel<T, DIM, NS>, threads, smem));
+    CFB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, interp_tile_kernel<T, DIM, NS, HORNER>, threads, smem));
     if (occ < 1) return 0;
     CFB_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(int), p.stream));
-    interp_tile_kernel<T, DIM, NS><<<p.num_sms * occ, threads, smem, p.stream>>>(a);
+    interp_tile_kernel<T, DIM, NS, HORNER><<<p.num_sms * occ, threads, smem, p.stream>>>(a);
     p.launches_exec++;
     CFB_CUDA_OK(cudaGetLastError());
     done = true;
     return 0;
 }
 
-template <typename T, int DIM, int NS>
-static int do_interp(Plan<T> &p, SIArgs<T> &a)
+template <typename T, int DIM, int NS, bool HORNER>
+static int do_interp_h(Plan<T> &p, SIArgs<T> &a)
 {
     bool done = false;
-    if (int e = do_interp_tile<T, DIM, NS>(p, a, done)) return e;
+    if (int e = do_interp_tile<T, DIM, NS, HORNER>(p, a, done)) return e;
     if (done) return 0;
     const size_t head = 18 * 16 * sizeof(T);
     const int warps = 8;
     size_t smem = head + warps * warp_scratch_bytes<T, DIM, NS>();
-    CFB_CUDA_OK(cudaFuncSetAttribute(interp_kernel<T, DIM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFB_CUDA_OK(cudaFuncSetAttribute(interp_kernel<T, DIM, NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long nb = (((long long)p.M + 255) / 256 * a.nt + warps - 1) / warps;
     long long cap = (long long)p.num_sms * 8;
     int blocks = (int)(nb < 1 ? 1 : (nb > cap ? cap : nb));
-    interp_kernel<T, DIM, NS><<<blocks, 32 * warps, smem, p.stream>>>(a);
+    interp_kernel<T, DIM, NS, HORNER><<<blocks, 32 * warps, smem, p.stream>>>(a);
     p.launches_exec++;
     CFB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// one instantiation per kernel evaluator (gpu_kerevalmeth 0: exp/sqrt, 1: Horner)
+template <typename T, int DIM, int NS>
+static int do_spread(Plan<T> &p, SIArgs<T> &a)
+{
+    return a.horner ? do_spread_h<T, DIM, NS, true>(p, a) : do_spread_h<T, DIM, NS, false>(p, a);
+}
+template <typename T, int DIM, int NS>
+static int do_interp(Plan<T> &p, SIArgs<T> &a)
+{
+    return a.horner ? do_interp_h<T, DIM, NS, true>(p, a) : do_interp_h<T, DIM, NS, false>(p, a);
 }
 
 template <typename T> struct max_ns;
@@ -140,7 +152,7 @@ struct NsDispatch {
         return NsDispatch<T, DIM, NS - 1>::interp(p, a);
     }
     static size_t scratch(int ns) {
-        if (ns == NS) return warp_scratch_bytes<T, DIM, NS>();
+        if (ns == NS) return warp_scratch_bytes<T, DIM, NS, false>();
         return NsDispatch<T, DIM, NS - 1>::scratch(ns);
     }
 };
