@@ -42,7 +42,44 @@ CONFIGS = {
     5: dict(name="cfg5: 3D type 2 fp64 512^3 (1024^3 fine grid) M=1e9 uniform tol=1e-9, z-slab partitioned", type=2,
             modes=(512, 512, 512), M=1_000_000_000, tol=1e-9, dtype="float64", dist="uniform", ntransf=1,
             opts=dict(gpu_method=1, gpu_sort=1), slab=True),
+    # not a BASELINE.json config: the type-1 twin of config 5, the path with the two collectives
+    # (ring halo add + all-reduce of the mode array) -- run with --config 6
+    6: dict(name="cfg5-type1: 3D type 1 fp64 512^3 (1024^3 fine grid) M=1e9 uniform tol=1e-9, z-slab partitioned", type=1,
+            modes=(512, 512, 512), M=1_000_000_000, tol=1e-9, dtype="float64", dist="uniform", ntransf=1,
+            opts=dict(gpu_method=2), slab=True),
 }
+
+
+SM_CLOCK_HZ = 1.965e9          # B200 boost clock the bench runs at (clocks.sm_mhz in the JSON line confirms it)
+
+
+def ncu_traffic(config_id):
+    """DRAM bytes of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[str(config_id)]["bytes"]
+    except Exception:   # noqa: BLE001
+        return None
+
+
+def binding_roofline(cfg, stage, ns, M, nt, k_ms, num_sms=148):
+    """The resource that actually bounds the dominant kernel: the HBM figure the
+    contract asks for says little for these kernels, so the line also carries this one.
+      interp (tile engine): every point reads its ns^d complex stencil values from shared memory:
+        shared-memory read bandwidth, peak 128 B/clk/SM;
+      spread: 2 ns^d FMAs per point on the FP32 (or FP64) pipe, peak 128 (64) FMA/clk/SM."""
+    d = len(cfg["modes"])
+    sF = 4 if cfg["dtype"] == "float32" else 8
+    if stage == "interp":
+        work = float(M) * nt * ns ** d * 2 * sF
+        peak = 128.0 * num_sms * SM_CLOCK_HZ
+        name, unit = "shared-memory read bandwidth", "GB/s"
+    else:
+        work = float(M) * nt * 2 * ns ** d
+        peak = (128.0 if sF == 4 else 64.0) * num_sms * SM_CLOCK_HZ
+        name, unit = "FP%d FMA pipe" % (8 * sF), "GFMA/s"
+    achieved = work / (k_ms * 1e-3)
+    return {"resource": name, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": unit, "frac": achieved / peak,
+            "peak_source": "nominal: per-SM rate x %d SMs x %.3f GHz" % (num_sms, SM_CLOCK_HZ / 1e9)}
 
 
 def algorithmic_bytes(cfg, stage):
@@ -234,7 +271,7 @@ def run_slab(args, cfg, rank, local_rank, world):
     replicated mode array).  Type 2 needs no collective (csrc/slab.cu)."""
     import torch
     import torch.distributed as dist
-    from cufinufft_b200.multi import SlabPlan, slab_type2
+    from cufinufft_b200.multi import SlabPlan, slab_type1, slab_type2
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -245,7 +282,8 @@ def run_slab(args, cfg, rank, local_rank, world):
     M_total = cfg["M"]
     M = M_total // world + (1 if rank < M_total % world else 0)
     stream = torch.cuda.current_stream()
-    plan = SlabPlan(2, shape, eps=cfg["tol"], dtype=npdt, rank=rank, world=world, gpu_device_id=local_rank, **cfg["opts"])
+    ttype = cfg["type"]
+    plan = SlabPlan(ttype, shape, eps=cfg["tol"], dtype=npdt, rank=rank, world=world, gpu_device_id=local_rank, **cfg["opts"])
     plan.set_stream(stream.cuda_stream)
     geo = plan.info()
     nf3, z0, z1 = geo["nf3"], geo["z0"], geo["z1"]
@@ -257,7 +295,17 @@ def run_slab(args, cfg, rank, local_rank, world):
     gk = torch.Generator(device=dev)
     gk.manual_seed(7)                                   # the mode array is REPLICATED: same seed on every rank
     fk = torch.view_as_complex((torch.rand(shape + (2,), generator=gk, device=dev, dtype=tdt) * 2 - 1).contiguous())
-    c = torch.zeros(M, dtype=cdt, device=dev)
+    if ttype == 2:
+        c = torch.zeros(M, dtype=cdt, device=dev)
+    else:
+        c = torch.view_as_complex((torch.rand((M, 2), generator=g, device=dev, dtype=tdt) * 2 - 1).contiguous())
+        fk.zero_()
+
+    def step(cc, ff):
+        if ttype == 2:
+            slab_type2(plan, cc, ff)
+        else:
+            slab_type1(plan, cc, ff)          # spread, ring halo add (NCCL), FFTs, all-reduce of the modes (NCCL)
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     plan.set_pts(z, y, x)
@@ -279,7 +327,7 @@ def run_slab(args, cfg, rank, local_rank, world):
 
     plan.set_timing(True)
     for _ in range(args.warmup):
-        slab_type2(plan, c, fk)
+        step(c, fk)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -287,14 +335,14 @@ def run_slab(args, cfg, rank, local_rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        slab_type2(plan, c, fk)
+        step(c, fk)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = plan.launch_counts()["execute"] * args.steps
+    launches = (plan.launch_counts()["execute"] + (1 if ttype == 1 else 0)) * args.steps
     stage_ms = []
     for _ in range(min(args.steps, 3)):
-        slab_type2(plan, c, fk)
+        step(c, fk)
         stage_ms.append(plan.timing())
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -304,7 +352,7 @@ def run_slab(args, cfg, rank, local_rank, world):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_step = float(tt.item()) / args.steps
     value = M_total / (ms_step * 1e-3)
-    checksum = float(torch.view_as_real(c).abs().sum().item())
+    checksum = float(torch.view_as_real(c if ttype == 2 else fk).abs().sum().item())
 
     e2e = None
     try:
@@ -316,10 +364,19 @@ def run_slab(args, cfg, rank, local_rank, world):
         fk_dev = torch.empty_like(fk)
         torch.cuda.synchronize()
 
+        c_dev = torch.empty_like(c)
+        if ttype == 1:
+            c_host.copy_(c)
+
         def e2e_step():
-            fk_dev.copy_(fk_host, non_blocking=True)
-            slab_type2(plan, c, fk_dev)
-            c_host.copy_(c, non_blocking=True)
+            if ttype == 2:
+                fk_dev.copy_(fk_host, non_blocking=True)
+                step(c, fk_dev)
+                c_host.copy_(c, non_blocking=True)
+            else:
+                c_dev.copy_(c_host, non_blocking=True)
+                step(c_dev, fk_dev)
+                fk_host.copy_(fk_dev, non_blocking=True)
             torch.cuda.synchronize()
         e2e_step()
         barrier()
@@ -333,9 +390,10 @@ def run_slab(args, cfg, rank, local_rank, world):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         ms_e2e = float(te.item()) / ksteps
-        e2e = {"value": M_total / (ms_e2e * 1e-3), "unit": "NU pts/s", "h2d_bytes_per_step": fk_host.numel() * 16,
-               "d2h_bytes_per_step": c_host.numel() * 16, "ms_per_step": ms_e2e,
-               "api": "per rank: pinned host fk -> device, cufinufft_slab_type2 (C ABI), c -> pinned host"}
+        nb_fk, nb_c = fk_host.numel() * 16, c_host.numel() * 16
+        e2e = {"value": M_total / (ms_e2e * 1e-3), "unit": "NU pts/s", "h2d_bytes_per_step": nb_fk if ttype == 2 else nb_c,
+               "d2h_bytes_per_step": nb_c if ttype == 2 else nb_fk, "ms_per_step": ms_e2e,
+               "api": "per rank: pinned host input -> device, cufinufft_slab_* stages (C ABI), result -> pinned host"}
     except Exception as exc:   # noqa: BLE001
         e2e = {"value": None, "error": repr(exc)}
 
@@ -357,18 +415,20 @@ def run_slab(args, cfg, rank, local_rank, world):
         "metric": "NU points/s per execute", "value": value, "unit": "NU pts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["name"], "type": 2, "modes": list(cfg["modes"]), "M_total": M_total, "M_per_gpu": M,
+        "config": {"workload": cfg["name"], "type": ttype, "modes": list(cfg["modes"]), "M_total": M_total, "M_per_gpu": M,
                    "tol": cfg["tol"], "ns": geo["ns"], "fine_grid": [geo["nf1"], geo["nf2"], nf3],
                    "slab_planes_rank0": [z0, z1], "halo_planes": geo["pad"], "points_outside_slab": outside,
                    "l2": "inputs larger than L2 (no flush needed)",
-                   "parallelism": "z-slab decomposition of the fine grid, points pre-binned by slab, mode array "
-                                  "replicated; type 2: no collective (halo planes are derived locally)"},
+                   "parallelism": "z-slab decomposition of the fine grid, points pre-binned by slab, mode array replicated; " +
+                                  ("type 2: no collective (halo planes are derived locally)" if ttype == 2 else
+                                   "type 1: ring halo add + all-reduce of the mode array over NCCL inside the timed step")},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "interp", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "interp" if ttype == 2 else "spread", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": k_ms,
-                     "note": "rank 0's interp launch; HBM roofline as the contract asks, the binding resource is the FP64 pipe "
-                             "and shared-memory bandwidth (DESIGN.md)"},
+                     "binding": binding_roofline(cfg, "interp" if ttype == 2 else "spread", geo["ns"], M, 1, k_ms),
+                     "note": "rank 0's interp launch; HBM roofline as the contract asks, `binding` is the resource that "
+                             "bounds the kernel (DESIGN.md)"},
         "stages_ms": stages, "setpts": {"ms": setpts_ms, "pts_per_s": M / (setpts_ms * 1e-3)},
         "checksum_abs_c_rank0": checksum, "cpu_baseline": None,
     }
@@ -548,10 +608,10 @@ def main():
     abytes = algorithmic_bytes(cfg_local, stage)
     achieved = abytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": stage, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": abytes, "kernel_ms": k_ms,
-                "note": "HBM roofline as the contract asks; the binding resource of this kernel is shared-memory/L1 "
-                        "wavefronts and the FP pipe (DESIGN.md)"}
+                "frac": achieved / peak, "traffic": ncu_traffic(args.config) if args.scale == 1.0 and not args.opt else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes, "kernel_ms": k_ms,
+                "binding": binding_roofline(cfg, stage, geo["ns"], M, min(ntransf, geo["maxbatch"]), k_ms),
+                "note": "HBM roofline as the contract asks; `binding` is the resource that bounds this kernel (DESIGN.md)"}
     stages = {k: float(np.median([s[k] for s in stage_ms])) for k in stage_ms[0]}
 
     line = {

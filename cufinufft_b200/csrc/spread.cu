@@ -122,8 +122,10 @@ void choose_internal_bins(Plan<T> &p, long long M)
         // halve one dimension (even, >= 8 cells): the one whose halved tile has the cheapest
         // bank-conflict-free layout, then the fewest cells (in 3-D that keeps x = 16 + halo = 22
         // cells, whose natural stride is conflict free for ns = 6, and halves y)
+        // (the density rule yields when the tile leaves fewer than four warps per SM: wide fp64
+        // stencils in 3-D, where one 130 KB tile per SM would serialise everything)
         const long long nib = (long long)p.nibins * 2;
-        if (M < 64 * nib || nib > (1LL << 28)) break;
+        if ((M < 64 * nib && p.sm_warps >= 4) || nib > (1LL << 28)) break;
         int best = -1;
         long long best_score = 0;
         for (int d = 0; d < p.dim; ++d) {

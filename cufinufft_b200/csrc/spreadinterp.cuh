@@ -83,7 +83,7 @@ template <typename T, int DIM, int NS> struct Geo {
     static constexpr int KP = VEC ? (((KP0 / V) | 1) * V) : (KP0 | 1);
     static constexpr int NACC = VEC ? WS : (DIM == 1 ? 1 : roundup(ITERS, 2));   // accumulator slots (padded passes have weight 0)
     static constexpr bool PREFETCH = NACC * (int)(sizeof(T) / 4) <= 16;  // next point's weights fetched one point ahead
-    static constexpr bool MERGE = NACC * (int)(sizeof(T) / 4) <= 72;      // run accumulators fit in registers
+    static constexpr bool MERGE = NACC * (int)(sizeof(T) / 4) <= 48;      // run accumulators (4 NACC 32-bit registers in fp64) fit in registers
     static constexpr bool TOFF_REGS = sizeof(T) == 4 || ITERS <= 16;      // per-pass tile offsets kept in registers
     static constexpr int SM_MAXW = ITERS * (int)(sizeof(T) / 4) > 24 ? 4 : 16;   // warps per SM-spread block (register budget)
 };
@@ -373,19 +373,22 @@ spread_sm_kernel(const SIArgs<T> a_in)
             if constexpr (G::MERGE) {
                 __syncwarp();
                 C *cell0 = tile + cur + ix;
-                C v[G::ITERS];
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it)
-                    if (active && it * G::R + r < G::ROWS) v[it] = cell0[tile_off(it)];
+                for (int c0 = 0; c0 < G::ITERS; c0 += 8) {       // eight passes' loads in flight at a time
+                    C v[8];
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it)
-                    if (active && it * G::R + r < G::ROWS) {
-                        const C d = acc.get(it);
-                        v[it].x += d.x; v[it].y += d.y;
-                    }
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < G::ITERS && active && (c0 + j) * G::R + r < G::ROWS) v[j] = cell0[tile_off(c0 + j)];
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it)
-                    if (active && it * G::R + r < G::ROWS) cell0[tile_off(it)] = v[it];
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < G::ITERS && active && (c0 + j) * G::R + r < G::ROWS) {
+                            const C d = acc.get(c0 + j);
+                            v[j].x += d.x; v[j].y += d.y;
+                        }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < G::ITERS && active && (c0 + j) * G::R + r < G::ROWS) cell0[tile_off(c0 + j)] = v[j];
+                }
                 acc.zero();
             }
         };
@@ -399,16 +402,21 @@ spread_sm_kernel(const SIArgs<T> a_in)
                 const C cv = sc.c[q];
                 const T cr = cv.x * k1, ci = cv.y * k1;
                 C *cell0 = tile + s_off[q] + ix;
-                C v[G::ITERS];
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it)
-                    if (active && it * G::R + r < G::ROWS) v[it] = cell0[tile_off(it)];
+                for (int c0 = 0; c0 < G::ITERS; c0 += 8) {
+                    C v[8];
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it)
-                    if (active && it * G::R + r < G::ROWS) { v[it].x = fma(cr, wq[it], v[it].x); v[it].y = fma(ci, wq[it], v[it].y); }
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < G::ITERS && active && (c0 + j) * G::R + r < G::ROWS) v[j] = cell0[tile_off(c0 + j)];
 #pragma unroll
-                for (int it = 0; it < G::ITERS; ++it)
-                    if (active && it * G::R + r < G::ROWS) cell0[tile_off(it)] = v[it];
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < G::ITERS && active && (c0 + j) * G::R + r < G::ROWS) {
+                            v[j].x = fma(cr, wq[c0 + j], v[j].x); v[j].y = fma(ci, wq[c0 + j], v[j].y);
+                        }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < G::ITERS && active && (c0 + j) * G::R + r < G::ROWS) cell0[tile_off(c0 + j)] = v[j];
+                }
             }
         };
 
@@ -478,16 +486,27 @@ spread_sm_kernel(const SIArgs<T> a_in)
                     const C cv = sc.c[q];
                     const T cr = cv.x * k1, ci = cv.y * k1;
                     C *cell0 = tile + s_off[q] + ix;
-#pragma unroll 4
-                    for (int it = 0; it < G::ITERS; ++it) {
-                        const int row = it * G::R + r;
-                        if (active && row < G::ROWS) {
+                    // four passes at a time: the loads of a chunk are issued before its first store
+                    for (int c0 = 0; c0 < G::ITERS; c0 += 4) {
+                        C v[4];
+                        T wg[4];
+                        C *cp[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int it = c0 + j, row = it * G::R + r;
+                            const bool on = it < G::ITERS && active && row < G::ROWS;
                             const int iz = row / NS, iy = row - iz * NS;
-                            const T wgt = DIM == 1 ? (T)1 : (DIM == 2 ? kq[G::NSX + r * G::WS + it] : kq[NS + iy] * kq[2 * NS + iz]);
-                            C *cell = cell0 + tile_off(it);
-                            C v = *cell;
-                            v.x = fma(cr, wgt, v.x); v.y = fma(ci, wgt, v.y);
-                            *cell = v;
+                            wg[j] = !on ? (T)0 : (DIM == 1 ? (T)1 : (DIM == 2 ? kq[G::NSX + r * G::WS + it] : kq[NS + iy] * kq[2 * NS + iz]));
+                            cp[j] = cell0 + (on ? tile_off(it) : 0);
+                            v[j] = on ? *cp[j] : C{0, 0};
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int it = c0 + j;
+                            if (it < G::ITERS && active && it * G::R + r < G::ROWS) {
+                                v[j].x = fma(cr, wg[j], v[j].x); v[j].y = fma(ci, wg[j], v[j].y);
+                                *cp[j] = v[j];
+                            }
                         }
                     }
                     __syncwarp();
