@@ -57,6 +57,7 @@ struct SIArgs {
     int sy, sz, tile_cells;     // padded tile strides
     int horner, ncoef;
     int zshift;                 // slab plans: local plane = global plane - zshift (0 otherwise)
+    int thr_num, thr_den;       // tuning override of the short-run threshold (0 = built-in; env CFB_DIRECT_THR=num/den)
     T es_c, es_beta;
     long long fwstride;
 };
@@ -77,8 +78,8 @@ template <typename T, int DIM, int NS> struct Geo {
     static constexpr bool PROD = DIM == 3 && NS <= 7 && sizeof(T) == 4;   // ky*kz products precomputed per point
     static constexpr bool VEC = DIM == 2 || PROD;
     static constexpr int NSX = VEC ? roundup(NS, V) : NS;
-    static constexpr int WS = roundup(ITERS, V);
-    static constexpr int KP0 = DIM == 1 ? NS : (VEC ? NSX + R * WS : 3 * NS);
+    static constexpr int WS = (VEC && ITERS == 1) ? 1 : roundup(ITERS, V);   // single-pass stencils: one weight per row slot
+    static constexpr int KP0 = DIM == 1 ? NS : (VEC ? NSX + roundup(R * WS, V) : 3 * NS);
     // VEC: KP/V odd (vector phase-A stores and phase-B loads conflict-free); else KP odd
     static constexpr int KP = VEC ? (((KP0 / V) | 1) * V) : (KP0 | 1);
     static constexpr int NACC = VEC ? WS : (DIM == 1 ? 1 : roundup(ITERS, 2));   // accumulator slots (padded passes have weight 0)
@@ -158,11 +159,18 @@ __device__ __forceinline__ void point_weights(const SIArgs<T> &a, const PtRec<T>
             if (DIM == 2) return ky[row];
             return ky[row % NS] * kz[row / NS];
         };
+        if constexpr (G::WS == 1) {
+            auto wr = [&](int r) -> float { return r < G::R ? wgt(r, 0) : 0.0f; };
 #pragma unroll
-        for (int r = 0; r < G::R; ++r)
+            for (int r0 = 0; r0 < G::R; r0 += 4)
+                dst[(G::NSX + r0) / 4] = make_float4(wr(r0), wr(r0 + 1), wr(r0 + 2), wr(r0 + 3));
+        } else {
 #pragma unroll
-            for (int it = 0; it < G::WS; it += 4)
-                dst[(G::NSX + r * G::WS + it) / 4] = make_float4(wgt(r, it), wgt(r, it + 1), wgt(r, it + 2), wgt(r, it + 3));
+            for (int r = 0; r < G::R; ++r)
+#pragma unroll
+                for (int it = 0; it < G::WS; it += 4)
+                    dst[(G::NSX + r * G::WS + it) / 4] = make_float4(wgt(r, it), wgt(r, it + 1), wgt(r, it + 2), wgt(r, it + 3));
+        }
     } else {
         // fp64 2-D: evaluate straight into the slots (no unrolling: the evaluation is long)
         kernel_vector<T, NS, false>(kp, x1, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
@@ -203,6 +211,8 @@ __device__ __forceinline__ void load_row_weights(const T *kq, int r, T (&w)[Geo<
     using G = Geo<T, DIM, NS>;
     if constexpr (DIM == 1) {
         w[0] = (T)1;
+    } else if constexpr (G::VEC && G::WS == 1) {
+        w[0] = kq[G::NSX + r];
     } else if constexpr (G::VEC) {
         using V16 = typename vec16<T>::type;
         const V16 *src = reinterpret_cast<const V16 *>(kq + G::NSX + r * G::WS);
@@ -253,6 +263,12 @@ template <int N> struct RunAcc<float, N> {
         asm("mov.b64 {%0, %1}, %2;" : "=f"(yl), "=f"(yh) : "l"(ay[it >> 1]));
         return (it & 1) ? make_float2(xh, yh) : make_float2(xl, yl);
     }
+};
+template <> struct RunAcc<float, 1> {          // single-pass stencils: plain scalar FMAs
+    float ax, ay;
+    __device__ __forceinline__ void zero() { ax = 0.0f; ay = 0.0f; }
+    __device__ __forceinline__ void fma(float cr, float ci, const float (&w)[1]) { ax = fmaf(cr, w[0], ax); ay = fmaf(ci, w[0], ay); }
+    __device__ __forceinline__ float2 get(int) const { return make_float2(ax, ay); }
 };
 template <int N> struct RunAcc<double, N> {
     double ax[N], ay[N];
@@ -392,16 +408,22 @@ spread_sm_kernel(const SIArgs<T> a_in)
                 acc.zero();
             }
         };
-        // one point applied to the tile at once (no run bookkeeping): loads of all passes first
-        auto apply_point = [&](int q) {
+        // one point applied to the tile at once (no run bookkeeping): loads of all passes first.
+        // (Fetching the operands one point ahead of the tile update was measured and did not pay:
+        // the kernel is issue-bound at this point, profiles/r01p: 62 % of the issue slots.)
+        auto fetch_point = [&](int q, T (&wq)[G::NACC], T &cr, T &ci, int &off) {
             if constexpr (G::MERGE) {
                 const T *kq = sc.ker + q * G::KP;
-                T wq[G::NACC];
                 load_row_weights<T, DIM, NS>(kq, r, wq);
                 const T k1 = active ? kq[ix] : (T)0;
                 const C cv = sc.c[q];
-                const T cr = cv.x * k1, ci = cv.y * k1;
-                C *cell0 = tile + s_off[q] + ix;
+                cr = cv.x * k1; ci = cv.y * k1;
+                off = s_off[q];
+            }
+        };
+        auto apply_point = [&](const T (&wq)[G::NACC], T cr, T ci, int off) {
+            if constexpr (G::MERGE) {
+                C *cell0 = tile + off + ix;
 #pragma unroll
                 for (int c0 = 0; c0 < G::ITERS; c0 += 8) {
                     C v[8];
@@ -446,15 +468,20 @@ spread_sm_kernel(const SIArgs<T> a_in)
                 if (lane == 0) prev = cur;
                 const unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && myoff != prev);
                 // Short runs (sparse regions): the run bookkeeping + flush costs more than it saves, the
-                // points of this batch go to the tile one by one.  Break-even run length from the
-                // instruction counts of both paths: (8 ITERS + 70) / (2.75 ITERS - 2); single-pass stencils: 8
-                // (below that the load -> add -> store dependence through one cell is cheaper than a flush).
-                constexpr int THR_NUM = G::ITERS > 1 ? 8 * G::ITERS + 70 : 8, THR_DEN = G::ITERS > 1 ? (11 * G::ITERS - 8) / 4 : 1;
-                if (__popc(starts) * THR_NUM > cnt * THR_DEN) {
+                // points of this batch go to the tile one by one.  Break-even mean run length, measured
+                // (tools/gpu_thr.sh, profiles/r01w): 3 points for multi-pass stencils, 8 for single-pass ones.
+                constexpr int THR_NUM = G::ITERS > 1 ? 3 : 8, THR_DEN = 1;
+                const int thr_num = a.thr_num > 0 ? a.thr_num : THR_NUM, thr_den = a.thr_num > 0 ? a.thr_den : THR_DEN;
+                if (__popc(starts) * thr_num > cnt * thr_den) {
                     if (cur >= 0) { flush_run(); cur = -1; }
                     __syncwarp();
 #pragma unroll 2
-                    for (int q = 0; q < cnt; ++q) apply_point(q);
+                    for (int q = 0; q < cnt; ++q) {
+                        T wq[G::NACC], cr, ci;
+                        int off;
+                        fetch_point(q, wq, cr, ci, off);
+                        apply_point(wq, cr, ci, off);
+                    }
                     __syncwarp();
                 } else {
                 // run by run: the accumulators live in registers across the tight inner loop (no

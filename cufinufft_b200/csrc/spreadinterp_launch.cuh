@@ -7,6 +7,7 @@
 // src/2d/interp2d_wrapper.cu:88-274 and the 1-D / 3-D twins): here ONE launch covers
 // all transforms of the batch.
 #pragma once
+#include <cstdlib>
 #include "spreadinterp.cuh"
 
 namespace cfb {
@@ -36,6 +37,11 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     a.horner = p.opts.gpu_kerevalmeth == 1; a.ncoef = p.horner_ncoef;
     a.es_c = p.es_c; a.es_beta = p.es_beta;
     a.zshift = p.slab ? p.zshift : 0;
+    a.thr_num = 0; a.thr_den = 1;
+    if (const char *e = getenv("CFB_DIRECT_THR")) {         // experiments only: "num/den" = run length below which a batch goes point by point
+        int n = 0, d = 1;
+        if (sscanf(e, "%d/%d", &n, &d) >= 1 && n > 0 && d > 0) { a.thr_num = n; a.thr_den = d; }
+    }
     a.fwstride = (long long)p.grid_cells();
     return a;
 }
