@@ -42,6 +42,9 @@ CONFIGS = {
     5: dict(name="cfg5: 3D type 2 fp64 512^3 (1024^3 fine grid) M=1e9 uniform tol=1e-9, z-slab partitioned", type=2,
             modes=(512, 512, 512), M=1_000_000_000, tol=1e-9, dtype="float64", dist="uniform", ntransf=1,
             opts=dict(gpu_method=1, gpu_sort=1), slab=True),
+    # config 4 names type 1 AND type 2: its type-2 half (tile interp, one launch per batch of 8)
+    7: dict(name="cfg4-type2: 2D type 2 fp32 512x512 radial M=262144 ntransf=64 tol=1e-4", type=2, modes=(512, 512),
+            M=262_144, tol=1e-4, dtype="float32", dist="radial", ntransf=64, opts=dict(gpu_method=1, gpu_sort=1), maxbatch=0),
     # not a BASELINE.json config: the type-1 twin of config 5, the path with the two collectives
     # (ring halo add + all-reduce of the mode array) -- run with --config 6
     6: dict(name="cfg5-type1: 3D type 1 fp64 512^3 (1024^3 fine grid) M=1e9 uniform tol=1e-9, z-slab partitioned", type=1,
@@ -489,7 +492,7 @@ def main():
     dim = len(cfg["modes"])
     M = cfg["M"]
     ntransf = cfg["ntransf"]
-    strong = args.config == 4 and world > 1
+    strong = args.config in (4, 7) and world > 1
     if strong:
         ntransf = cfg["ntransf"] // world            # shard the batch by transform, no collective
     shape = tuple(cfg["modes"])[::-1]

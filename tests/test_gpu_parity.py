@@ -89,3 +89,43 @@ def test_transform_vs_oracle(case):
         scale = np.abs(exact).max()
     floor = 3e-6 if dtype == np.float32 else 1e-13
     assert np.abs(got - exact).max() / scale <= max(10 * tol, floor)
+
+
+# Inputs dense enough for setpts to split the reference's bins into internal sub-bins (one or more
+# halvings, csrc/spread.cu: choose_internal_bins) and distributions that exercise both the
+# run-merged and the point-by-point paths of the SM spread kernel.  The reference-facing bin arrays
+# must stay bit-exact, the transform within the parity tolerance.
+SUBBIN_CASES = [
+    # (modes, M, tol, dtype, dist, opts)
+    ((128, 96), 400000, 1e-3, np.float32, "uniform", {}),
+    ((100, 80), 300000, 1e-4, np.float32, "cluster", {}),                     # nf not a multiple of the bins
+    ((64, 64), 60000, 1e-4, np.float32, "onebin", {}),                        # every point in one bin: long runs
+    ((32, 32, 32), 300000, 1e-5, np.float32, "uniform", {}),
+    ((24, 20, 16), 200000, 1e-5, np.float32, "cluster", dict(gpu_maxsubprobsize=300)),
+    ((20, 18, 16), 150000, 1e-9, np.float64, "uniform", {}),                  # wide fp64 stencil: MERGE = false path
+    ((48, 40), 200000, 1e-9, np.float64, "cluster", {}),
+]
+
+
+@pytest.mark.parametrize("case", SUBBIN_CASES, ids=lambda c: "%s-M%d-%s-%s" % ("x".join(map(str, c[0])), c[1], np.dtype(c[3]).name, c[4]))
+def test_type1_with_internal_subbins(case):
+    modes, M, tol, dtype, dist, opts = case
+    dim = len(modes)
+    pts = make_points(M, dim, dtype, seed=77, dist=dist)
+    data = make_strengths(M, dtype)
+    out, plan = gpu_nufft(1, modes, pts, data, tol, dtype, return_plan=True, **opts)
+    ref = orc.nufft(1, modes, pts, data[0], tol, dtype=dtype)
+    err = rel_l2(out[0], ref)
+    assert err <= TOL_PARITY[dtype], err
+    _check_bins(plan, pts, dtype, opts.get("gpu_maxsubprobsize", 1024))
+    # a second setpts with few points on the same plan falls back to the reference's bins
+    few = [p[:500].copy() for p in pts]
+    from cufinufft_b200 import gpuarray
+    dev = [gpuarray.to_gpu(p) for p in few]
+    plan.set_pts(*dev[::-1])
+    cg = gpuarray.to_gpu(np.ascontiguousarray(data[:, :500]))
+    fkg = gpuarray.zeros((1,) + tuple(modes)[::-1], cdtype(dtype))
+    plan.execute(cg, fkg)
+    ref2 = orc.nufft(1, modes, few, data[0, :500], tol, dtype=dtype)
+    assert rel_l2(fkg.get()[0], ref2) <= TOL_PARITY[dtype]
+    _check_bins(plan, few, dtype, opts.get("gpu_maxsubprobsize", 1024))
