@@ -4,7 +4,8 @@
 // Reference kernels replaced (all of src/{1,2,3}d/spreadinterp{1,2,3}d.cu):
 //   Spread_{1,2,3}d_NUptsdriven[_Horner]  -> spread_gm_kernel   (gpu_method 1, GM / GM-sort)
 //   Spread_{1,2,3}d_Subprob[_Horner]      -> spread_sm_kernel   (gpu_method 2, SM)
-//   Interp_{1,2,3}d_NUptsdriven[_Horner], Interp_{2,3}d_Subprob[_Horner] -> interp_kernel
+//   Interp_{1,2,3}d_NUptsdriven[_Horner]  -> interp_kernel      (gather engine)
+//   Interp_{2,3}d_Subprob[_Horner]        -> interp_tile_kernel (tile engine, the default when sorted)
 //
 // Design (DESIGN.md "spread" / "interp").  The reference gives every point to one thread that
 // does 2*ns^d scalar atomics (shared or global).  Here
@@ -13,23 +14,27 @@
 //    Horner), the strength gather (prefetched one batch ahead), all parked in a small per-warp
 //    scratch.  Phase B is lane-per-cell: the 32 lanes are laid over the point's stencil,
 //    lane = (row r, column ix), ITERS passes cover all rows.
-//  * setpts sorts points by (bin, stencil origin), so consecutive points usually share their
-//    WHOLE stencil.  Such a RUN is accumulated in registers (ITERS complex accumulators per
+//  * setpts sorts points by (bin, sub-bin, stencil origin), so consecutive points usually share
+//    their WHOLE stencil.  Such a RUN is accumulated in registers (ITERS complex accumulators per
 //    lane, packed f32x2 FMAs in fp32) and touches memory once per run instead of once per point:
-//      spread SM : run -> warp-private padded bin tile in shared memory with plain LDS/FADD/STS
+//      spread SM : run -> warp-private padded tile in shared memory with plain LDS/FADD/STS
 //                  (lanes of one flush hit distinct cells, padded strides keep them on distinct
 //                  banks: no shared atomics at all); tile -> fine grid once per subproblem with
-//                  vector RED (red.global.add.v2.f32) over the touched rows only, cleared on the way
+//                  vector RED (red.global.add.v2.f32) over the touched box, cleared on the way.
+//                  Batches whose runs are short (sparse regions) skip the run bookkeeping and
+//                  apply their points to the tile one by one; the choice is per batch.
 //      spread GM : run -> fine grid directly with vector RED
-//      interp    : the stencil's grid values are loaded once per run (coalesced row segments)
-//                  and reused from registers for every point of the run; the 32 per-lane partial
-//                  sums of 8 points are transposed through shared memory and reduced together
-//    With one point per run this degenerates to the per-point version; clustered inputs (the
-//    reference's worst case: atomic contention) become the best case.
-//  * Subproblems (the reference's (bin, <= maxsubprobsize points) units, same subprob_to_bin
-//    map) x transforms are pulled from a global work counter by persistent warps.
-// Stencils too large for register accumulators (3-D fp64, ns >= 11) use the same kernels with
-// MERGE = false: every pass is applied to memory immediately.
+//      interp (gather engine): the stencil's grid values are loaded once per run (coalesced row
+//                  segments) and reused from registers for every point of the run; the per-lane
+//                  partial sums of 8 points are transposed through shared memory and reduced together
+//  * Work items = subproblems (<= maxsubprobsize consecutive sorted points of one INTERNAL bin: the
+//    reference's bin or a sub-bin of it, setpts.cu / spread.cu) x transforms, pulled from a global
+//    work counter by persistent warps (spread) or blocks (tile interp).
+//  * The tile interpolation engine (interp_tile_kernel, below) stages the bin's grid tile in shared
+//    memory with cp.async and is thread-per-point.
+// Stencils too large for register accumulators (3-D fp64, ns >= 9) use the same kernels with
+// MERGE = false: every pass is applied to memory immediately (four passes' loads at a time).
+// Every kernel is instantiated per evaluator (HORNER): the other evaluator's code is not emitted.
 #pragma once
 #include "cfb_device.cuh"
 
@@ -83,7 +88,6 @@ template <typename T, int DIM, int NS> struct Geo {
     // VEC: KP/V odd (vector phase-A stores and phase-B loads conflict-free); else KP odd
     static constexpr int KP = VEC ? (((KP0 / V) | 1) * V) : (KP0 | 1);
     static constexpr int NACC = VEC ? WS : (DIM == 1 ? 1 : roundup(ITERS, 2));   // accumulator slots (padded passes have weight 0)
-    static constexpr bool PREFETCH = NACC * (int)(sizeof(T) / 4) <= 16;  // next point's weights fetched one point ahead
     static constexpr bool MERGE = NACC * (int)(sizeof(T) / 4) <= 48;      // run accumulators (4 NACC 32-bit registers in fp64) fit in registers
     static constexpr bool TOFF_REGS = sizeof(T) == 4 || ITERS <= 16;      // per-pass tile offsets kept in registers
     static constexpr int SM_MAXW = ITERS * (int)(sizeof(T) / 4) > 24 ? 4 : 16;   // warps per SM-spread block (register budget)

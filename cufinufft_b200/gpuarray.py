@@ -42,6 +42,10 @@ def device_count():
     return n.value if code == 0 else 0
 
 
+def set_device(dev):
+    _check(runtime().cudaSetDevice(c_int(int(dev))))
+
+
 def synchronize():
     _check(runtime().cudaDeviceSynchronize())
 
@@ -69,7 +73,16 @@ class GPUArray:
         self.ptr = self._alloc.ptr + _offset
 
     def __getitem__(self, i):
-        """Leading-axis integer index -> contiguous view (what `k_gpu[0]` needs)."""
+        """Leading-axis integer index -> contiguous view (what `k_gpu[0]` needs); a unit-stride
+        slice of the leading axis -> contiguous view (what `k_gpu[1][:4]` needs)."""
+        if isinstance(i, slice):
+            start, stop, step = i.indices(self.shape[0])
+            if step != 1:
+                raise IndexError("only unit-stride slices are supported")
+            n = max(stop - start, 0)
+            row = (int(np.prod(self.shape[1:])) if len(self.shape) > 1 else 1) * self.dtype.itemsize
+            return GPUArray((n,) + self.shape[1:], self.dtype, _base=self._alloc,
+                            _offset=(self.ptr - self._alloc.ptr) + start * row)
         if not isinstance(i, (int, np.integer)) or len(self.shape) < 2:
             raise IndexError("only leading-axis integer views are supported")
         i = int(i) % self.shape[0]
