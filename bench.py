@@ -616,6 +616,10 @@ def main():
                 "binding": binding_roofline(cfg, stage, geo["ns"], M, min(ntransf, geo["maxbatch"]), k_ms),
                 "note": "HBM roofline as the contract asks; `binding` is the resource that bounds this kernel (DESIGN.md)"}
     stages = {k: float(np.median([s[k] for s in stage_ms])) for k in stage_ms[0]}
+    # the HBM-bound stage of the path (deconvolve | amplify): algorithmic bytes / live duration vs the measured copy peak
+    dstage = "deconvolve" if cfg["type"] == 1 else "amplify"
+    d_gbs = algorithmic_bytes(cfg_local, dstage) / (max(stages["deconv_amplify_ms"], 1e-6) * 1e-3) / 1e9
+    stages_hbm = {dstage: {"achieved_gbs": d_gbs, "frac": d_gbs / peak}}
 
     line = {
         "metric": "NU points/s per execute", "value": value, "unit": "NU pts/s", "n_gpus": world, "steps": args.steps,
@@ -628,7 +632,8 @@ def main():
                    "parallelism": "one independent transform per rank (batch sharded by transform, no collective)"
                    if not strong else "ntransf sharded by transform across ranks, no collective"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-        "stages_ms": stages, "setpts": {"ms": setpts_ms, "pts_per_s": M / (setpts_ms * 1e-3), "launches": setpts_launches,
+        "stages_ms": stages, "stages_hbm": stages_hbm,
+        "setpts": {"ms": setpts_ms, "pts_per_s": M / (setpts_ms * 1e-3), "launches": setpts_launches,
                                         "hbm_frac": algorithmic_bytes(cfg, "setpts") / (setpts_ms * 1e-3) / 1e9 / peak},
     }
     if not args.no_cpu_baseline and world == 1:
