@@ -82,6 +82,8 @@ struct Plan {
     int ibs[3] = {1, 1, 1};
     int spb[3] = {1, 1, 1};
     int nibins = 1;
+    int imaxsub = 1024;                  // points per work item of the internal list (>= gpu_maxsubprobsize)
+    bool ilist = false;                  // the engines use their own work list (isubstart / is2b) instead of the reference's
     DevBuf isubstart, is2b;              // internal subproblem offsets [nibins+1] and map (unused when ibs == bs)
     // points (borrowed) + derived (owned)
     int M = -1;

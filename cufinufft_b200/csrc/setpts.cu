@@ -389,16 +389,16 @@ static int setpts_dim(Plan<T> &p)
     int maxslots = p.nbins + M / p.opts.gpu_maxsubprobsize + 1;
     map_subprob_kernel<<<(maxslots + 255) / 256, 256, 0, st>>>(p.nbins, maxslots, substart, scal, s2b);
     p.launches_setpts++;
-    if (g.spbt > 1) {
-        // the tile engines' own work list over the internal bins (same construction, finer bins)
+    if (p.ilist) {
+        // the tile engines' own work list over the internal bins (same construction, finer bins / larger items)
         int *isub = p.isubstart.template as<int>();
         const long long nis = (long long)p.nibins + 1;
         const int itiles = (int)((nis + SCAN_TILE - 1) / SCAN_TILE);
-        isub_count_kernel<<<(int)((nis + 255) / 256), 256, 0, st>>>(p.nibins, g.cpb, p.opts.gpu_maxsubprobsize, keyoff, isub);
+        isub_count_kernel<<<(int)((nis + 255) / 256), 256, 0, st>>>(p.nibins, g.cpb, p.imaxsub, keyoff, isub);
         scan_reduce_kernel<<<itiles, SCAN_THREADS, 0, st>>>(nis, isub, tilesum);
         scan_top_kernel<<<1, 1024, 0, st>>>(itiles, tilesum);
         scan_apply_kernel<<<itiles, SCAN_THREADS, 0, st>>>(nis, isub, tilesum);
-        int islots = p.nibins + M / p.opts.gpu_maxsubprobsize + 1;
+        int islots = p.nibins + M / p.imaxsub + 1;
         map_subprob_kernel<<<(islots + 255) / 256, 256, 0, st>>>(p.nibins, islots, isub, isub + p.nibins, p.is2b.template as<int>());
         p.launches_setpts += 5;
     }
@@ -445,9 +445,9 @@ int stage_setpts(Plan<T> &p)
     }
     size_t maxslots = (size_t)p.nbins + M / (size_t)p.opts.gpu_maxsubprobsize + 1;
     CFB_CUDA_OK(p.subprob_to_bin.reserve(maxslots * sizeof(int)));
-    if (g.spbt > 1) {
+    if (p.ilist) {
         CFB_CUDA_OK(p.isubstart.reserve(((size_t)p.nibins + 1 + 4) * sizeof(int)));
-        CFB_CUDA_OK(p.is2b.reserve(((size_t)p.nibins + M / (size_t)p.opts.gpu_maxsubprobsize + 1) * sizeof(int)));
+        CFB_CUDA_OK(p.is2b.reserve(((size_t)p.nibins + M / (size_t)p.imaxsub + 1) * sizeof(int)));
     }
     p.idx_valid = false;
     switch (p.dim) {

@@ -109,8 +109,18 @@ void choose_internal_bins(Plan<T> &p, long long M)
 {
     for (int d = 0; d < 3; ++d) { p.ibs[d] = p.bs[d]; p.spb[d] = 1; }
     p.nibins = p.nbins;
+    p.imaxsub = p.opts.gpu_maxsubprobsize;
+    p.ilist = false;
     plan_tile_geometry(p);
     if (!(p.type == 1 && p.method == 2 && p.sorted) || p.dim == 1) return;
+    // Work-item size of the engines' own list: every item ends with a flush of its tile to the fine
+    // grid (15 % of the config-3 kernel's instructions with 1024-point items), so dense inputs get
+    // items of up to 4096 points -- as long as >= 16 items per resident warp remain for balance.
+    {
+        const long long per_item = M / (16LL * p.num_sms * 16);
+        const long long lo = p.opts.gpu_maxsubprobsize, hi = 4096;
+        p.imaxsub = (int)(per_item < lo ? lo : (per_item > hi ? (hi > lo ? hi : lo) : per_item));
+    }
     const size_t target = 14 * 1024;
     for (;;) {
         size_t per_warp;
@@ -140,6 +150,7 @@ void choose_internal_bins(Plan<T> &p, long long M)
         p.ibs[best] /= 2; p.spb[best] *= 2; p.nibins = (int)nib;
         plan_tile_geometry(p);
     }
+    p.ilist = p.nibins != p.nbins || p.imaxsub != p.opts.gpu_maxsubprobsize;
 }
 
 template int stage_spread<float>(Plan<float> &, const float2 *, float2 *, int);

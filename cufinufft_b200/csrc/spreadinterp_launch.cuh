@@ -18,14 +18,14 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     SIArgs<T> a;
     a.recs = p.recs.template as<PtRec<T>>();
     a.c = nullptr; a.fw = nullptr;
-    const bool split = p.nibins != p.nbins;             // internal bins finer than the reference's (setpts.cu)
+    const bool split = p.ilist;                         // the engines' own work list (finer bins and/or larger items, setpts.cu)
     a.keyoff = p.keyoff.template as<int>(); a.cpb = p.sortgeo.cpb;
     a.s2b = split ? p.is2b.template as<int>() : p.subprob_to_bin.template as<int>();
     a.substart = split ? p.isubstart.template as<int>() : p.subprobstartpts.template as<int>();
     a.nsub = split ? p.isubstart.template as<int>() + p.nibins : p.scalars.template as<int>();
     a.counter = p.scalars.template as<int>() + 1;
     a.hcoef = p.hcoef.template as<T>();
-    a.M = p.M; a.nt = nt; a.maxsub = p.opts.gpu_maxsubprobsize;
+    a.M = p.M; a.nt = nt; a.maxsub = p.ilist ? p.imaxsub : p.opts.gpu_maxsubprobsize;
     a.nf1 = p.nf1; a.nf2 = p.nf2; a.nf3 = p.nf3;
     a.bs1 = p.ibs[0]; a.bs2 = p.ibs[1]; a.bs3 = p.ibs[2]; a.nb1 = p.nbin[0]; a.nb2 = p.nbin[1];
     a.rbs1 = p.bs[0]; a.rbs2 = p.bs[1]; a.rbs3 = p.bs[2];
