@@ -321,6 +321,7 @@ def run_slab(args, cfg, rank, local_rank, world):
         torch.cuda.synchronize()
         t_set.append(ev[0].elapsed_time(ev[1]))
     setpts_ms = float(np.median(t_set))
+    setpts_launches = plan.launch_counts()["setpts"]
     outside = plan.info()["outside"]
 
     def barrier():
@@ -432,7 +433,7 @@ def run_slab(args, cfg, rank, local_rank, world):
                      "binding": binding_roofline(cfg, "interp" if ttype == 2 else "spread", geo["ns"], M, 1, k_ms),
                      "note": "rank 0's interp launch; HBM roofline as the contract asks, `binding` is the resource that "
                              "bounds the kernel (DESIGN.md)"},
-        "stages_ms": stages, "setpts": {"ms": setpts_ms, "pts_per_s": M / (setpts_ms * 1e-3)},
+        "stages_ms": stages, "setpts": {"ms": setpts_ms, "pts_per_s": M / (setpts_ms * 1e-3), "launches": setpts_launches},
         "checksum_abs_c_rank0": checksum, "cpu_baseline": None,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -95,6 +95,7 @@ for _sfx, _real in (("", c_double), ("f", c_float)):
         get_timing=_bind("cufinufft%s_get_timing" % _sfx, [c_void_p, c_void_p]),
         get_launch_counts=_bind("cufinufft%s_get_launch_counts" % _sfx, [c_void_p, c_void_p]),
         set_interp_engine=_bind("cufinufft%s_set_interp_engine" % _sfx, [c_void_p, c_int]),
+        set_sort_levels=_bind("cufinufft%s_set_sort_levels" % _sfx, [c_void_p, c_int]),
         # z-slab decomposition of one 3-D transform
         slab_make_plan=_bind("cufinufft%s_slab_makeplan" % _sfx,
                              [c_int, c_int_p, c_int, _real, c_int, c_int, POINTER(c_void_p), NufftOpts_p]),
@@ -124,6 +125,6 @@ C_ABI_SYMBOLS = [base % s for s in ("", "f") for base in (
 EXTENSION_SYMBOLS = ["cufinufft_b200_version", "cufinufft_b200_host_params", "cufinufft_b200_phihat_quadrature"] + [base % s for s in ("", "f") for base in (
     "cufinufft%s_set_stream", "cufinufft%s_setpts_host", "cufinufft%s_execute_host", "cufinufft%s_spread",
     "cufinufft%s_interp", "cufinufft%s_get_ints", "cufinufft%s_get_reals", "cufinufft%s_set_timing",
-    "cufinufft%s_get_timing", "cufinufft%s_get_launch_counts", "cufinufft%s_set_interp_engine",
+    "cufinufft%s_get_timing", "cufinufft%s_get_launch_counts", "cufinufft%s_set_interp_engine", "cufinufft%s_set_sort_levels",
     "cufinufft%s_slab_makeplan", "cufinufft%s_slab_info", "cufinufft%s_slab_type2", "cufinufft%s_slab_type1_spread",
     "cufinufft%s_slab_halo_pack", "cufinufft%s_slab_halo_add", "cufinufft%s_slab_type1_finish")]

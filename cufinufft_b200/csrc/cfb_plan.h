@@ -50,6 +50,10 @@ struct SortGeo {
     // reference bin and dimension; internal bin = refbin * spbt + sub, so the reference's bin-major
     // order is kept and its arrays are sums over groups of spbt internal bins
     int ibs[3], spb[3], spbt;
+    // stencil-origin cells per internal bin and dimension (the "fine" part of the order).  Either
+    // they are part of the global key (nk = nkf, cpb = cpbf) or the global key is the bin alone
+    // (nk = 1, cpb = 1) and every work item is sorted by cell afterwards (local_sort_kernel)
+    int nkf[3], cpbf;
     int nk[3];      // distinct stencil origins per bin and dimension (1 = key is the bin alone)
     int cpb;        // nk[0]*nk[1]*nk[2]
     int ns;
@@ -93,6 +97,8 @@ struct Plan {
     DevBuf keyoff, tilesum;              // int[nkeys+1] key histogram -> offsets; scan scratch
     SortGeo sortgeo;
     bool fine_sort_allowed = true;
+    bool local_sort = false;             // two-level order: bins globally, stencil cells per work item
+    int sort_levels = 0;                 // 0 automatic, 1 / 2 forced (cufinufft*_set_sort_levels: tests, A/B)
     bool idx_valid = false;
     DevBuf binsize, binstartpts, numsubprob, subprobstartpts, subprob_to_bin;
     DevBuf scalars;                      // int[8]: [0] totalnumsubprob, [1] work counter, ...
@@ -107,6 +113,7 @@ struct Plan {
     int device = 0;
     int num_sms = 148;
     int max_smem_optin = 227 * 1024;
+    long long l2_bytes = 126LL << 20;
     // SM-tile geometry (set at makeplan)
     int tile_pad = 0;                    // ceil(ns/2)
     int tile_sy = 0, tile_sz = 0;        // padded strides (cells)

@@ -185,6 +185,7 @@ static int makeplan(int type, int dim, int *nmodes, int iflag, int ntransf, T to
     if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) { delete p; return CFB_ERR_CUDA; }
     p->num_sms = prop.multiProcessorCount;
     p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    p->l2_bytes = prop.l2CacheSize;
     plan_tile_geometry(*p);
 
     auto fail = [&](int code) { free_plan(p); return code; };
@@ -574,6 +575,8 @@ int cufinufft_get_timing(cufinufft_plan plan, float *out) { return cfb::get_timi
 int cufinufftf_get_timing(cufinufftf_plan plan, float *out) { return cfb::get_timing<float>(PD(plan), out); }
 int cufinufft_set_interp_engine(cufinufft_plan plan, int e) { if (!PD(plan) || e < 0 || e > 2) return CFB_ERR_BAD_ARG; plan->p->interp_engine = e; return 0; }
 int cufinufftf_set_interp_engine(cufinufftf_plan plan, int e) { if (!PD(plan) || e < 0 || e > 2) return CFB_ERR_BAD_ARG; plan->p->interp_engine = e; return 0; }
+int cufinufft_set_sort_levels(cufinufft_plan plan, int l) { if (!PD(plan) || l < 0 || l > 2) return CFB_ERR_BAD_ARG; plan->p->sort_levels = l; return 0; }
+int cufinufftf_set_sort_levels(cufinufftf_plan plan, int l) { if (!PD(plan) || l < 0 || l > 2) return CFB_ERR_BAD_ARG; plan->p->sort_levels = l; return 0; }
 int cufinufft_get_launch_counts(cufinufft_plan plan, int *o) { if (!PD(plan) || !o) return CFB_ERR_BAD_ARG; o[0] = plan->p->launches_setpts; o[1] = plan->p->launches_exec; return 0; }
 int cufinufftf_get_launch_counts(cufinufftf_plan plan, int *o) { if (!PD(plan) || !o) return CFB_ERR_BAD_ARG; o[0] = plan->p->launches_setpts; o[1] = plan->p->launches_exec; return 0; }
 

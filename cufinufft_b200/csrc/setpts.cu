@@ -14,9 +14,10 @@
 //   K1 key_count     key = bin * cells_per_bin + stencil cell inside the bin; warp-aggregated
 //                    (match_any) histogram atomics return the rank of each point in its key
 //   K2 scan_reduce / scan_top / scan_apply   three-phase exclusive scan of the key counts
-//   K3 bins_from_keys  binsize[b] = off[(b+1)*cpb] - off[b*cpb]
-//   K4 scan_bins     binstartpts, integer ceil-div subproblem counts, their inclusive scan and
-//                    totalnumsubprob (device scalar)
+//   K3 ref_bins     binsize[b] = off[(b+1)*cpb] - off[b*cpb], binstartpts[b] = off[b*cpb], integer
+//                    ceil-div subproblem counts
+//   K4 the same three-phase scan over the subproblem counts -> subprobstartpts, totalnumsubprob
+//                    (device scalar)
 //   K5 map_subprob   one thread per subproblem slot, binary search in subprobstartpts
 //   K6 place_points  ONE 16-byte (fp32) / 32-byte (fp64) record per point
 //                    {x_rescaled, y_rescaled, z_rescaled, original index} scattered to its sorted
@@ -83,24 +84,38 @@ __device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__res
 
 // K1: histogram + rank.  Lanes of a warp that fall on the same key are aggregated into
 // one atomicAdd (clustered inputs put most of a warp on one key).
+// Four points per thread and iteration: the twelve coordinate loads are in flight together, then the
+// four histogram atomics, then the four rank stores (one point per iteration left the kernel at the
+// latency of load -> atomic -> store chains: 1.7 TB/s with every table L2-resident, profiles/r02i).
+constexpr int SP_UNROLL = 4;
+
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 key_count_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
                  const SortGeo g, int *__restrict__ keycnt, int *__restrict__ rank, int *__restrict__ outside)
 {
     const int lane = threadIdx.x & 31;
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < M; base += (long long)gridDim.x * blockDim.x) {
-        int i = (int)(base + threadIdx.x);
-        bool valid = i < M;
-        T xr, yr, zr;
-        int k = valid ? point_key<T, DIM>(x, y, z, i, g, xr, yr, zr, outside) : -1 - lane;
-        unsigned peers = __match_any_sync(0xffffffffu, k);
-        int leader = __ffs(peers) - 1;
-        int rank_in_group = __popc(peers & ((1u << lane) - 1));
-        int basecnt = 0;
-        if (valid && lane == leader) basecnt = atomicAdd(&keycnt[k], __popc(peers));
-        basecnt = __shfl_sync(0xffffffffu, basecnt, leader);
-        if (valid) rank[i] = basecnt + rank_in_group;
+    const long long span = (long long)blockDim.x * SP_UNROLL;
+    for (long long base = (long long)blockIdx.x * span; base < M; base += (long long)gridDim.x * span) {
+        int k[SP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SP_UNROLL; ++u) {
+            const long long i = base + (long long)u * blockDim.x + threadIdx.x;
+            T xr, yr, zr;
+            k[u] = i < M ? point_key<T, DIM>(x, y, z, (int)i, g, xr, yr, zr, outside) : -1 - lane;
+        }
+#pragma unroll
+        for (int u = 0; u < SP_UNROLL; ++u) {
+            const long long i = base + (long long)u * blockDim.x + threadIdx.x;
+            const bool valid = i < M;
+            const unsigned peers = __match_any_sync(0xffffffffu, k[u]);
+            const int leader = __ffs(peers) - 1;
+            const int rank_in_group = __popc(peers & ((1u << lane) - 1));
+            int basecnt = 0;
+            if (valid && lane == leader) basecnt = atomicAdd(&keycnt[k[u]], __popc(peers));
+            basecnt = __shfl_sync(0xffffffffu, basecnt, leader);
+            if (valid) rank[i] = basecnt + rank_in_group;
+        }
     }
 }
 
@@ -204,61 +219,19 @@ scan_apply_kernel(long long n, int *__restrict__ a, const int *__restrict__ tile
     }
 }
 
-// K3: bin counts from the key offsets (keyoff has nkeys+1 entries, keyoff[nkeys] = M)
+// K3+K4 (multi-block): per reference bin its size, its start (= the key offset), its subproblem count
+// (integer ceil: the reference's float ceil drops the last subproblem above 2^24 points per bin,
+// precision_independent.cu:71); the counts are then scanned in place into subprobstartpts.
 __global__ void __launch_bounds__(256)
-bins_from_keys_kernel(int nbins, int cpb, const int *__restrict__ keyoff, int *__restrict__ binsize)
+ref_bins_kernel(int nbins, int cpb, int maxsub, const int *__restrict__ keyoff, int *__restrict__ binsize,
+                int *__restrict__ binstartpts, int *__restrict__ numsubprob, int *__restrict__ subprobstartpts)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nbins) binsize[b] = keyoff[(size_t)(b + 1) * cpb] - keyoff[(size_t)b * cpb];
-}
-
-// K4: one block walks the bins in chunks of blockDim.x with a running carry.  Produces
-// binstartpts (exclusive), numsubprob = ceil(binsize/maxsub) (integer: the reference's float
-// ceil drops the last subproblem above 2^24 points per bin, precision_independent.cu:71),
-// subprobstartpts (inclusive scan with leading 0) and scalars[0] = totalnumsubprob.
-__global__ void __launch_bounds__(1024)
-scan_bins_kernel(int nbins, int maxsub, const int *__restrict__ binsize, int *__restrict__ binstartpts,
-                 int *__restrict__ numsubprob, int *__restrict__ subprobstartpts, int *__restrict__ scalars)
-{
-    __shared__ int wsum_a[32], wsum_b[32];
-    __shared__ int carry_a, carry_b;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (threadIdx.x == 0) { carry_a = 0; carry_b = 0; subprobstartpts[0] = 0; }
-    __syncthreads();
-    for (int base = 0; base < nbins; base += blockDim.x) {
-        int b = base + threadIdx.x;
-        int cnt = b < nbins ? binsize[b] : 0;
-        int nsp = (cnt + maxsub - 1) / maxsub;
-        int sa = cnt, sb = nsp;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
-            if (lane >= o) { sa += ta; sb += tb; }
-        }
-        if (lane == 31) { wsum_a[wid] = sa; wsum_b[wid] = sb; }
-        __syncthreads();
-        if (wid == 0) {
-            int va = lane < nw ? wsum_a[lane] : 0, vb = lane < nw ? wsum_b[lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int ta = __shfl_up_sync(0xffffffffu, va, o), tb = __shfl_up_sync(0xffffffffu, vb, o);
-                if (lane >= o) { va += ta; vb += tb; }
-            }
-            wsum_a[lane] = va; wsum_b[lane] = vb;   // inclusive over warps
-        }
-        __syncthreads();
-        int offa = carry_a + (wid ? wsum_a[wid - 1] : 0);
-        int offb = carry_b + (wid ? wsum_b[wid - 1] : 0);
-        if (b < nbins) {
-            binstartpts[b] = offa + sa - cnt;
-            numsubprob[b] = nsp;
-            subprobstartpts[b + 1] = offb + sb;
-        }
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) { carry_a = offa + sa; carry_b = offb + sb; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) scalars[0] = carry_b;
+    if (b < nbins) {
+        const int p0 = keyoff[(size_t)b * cpb], cnt = keyoff[(size_t)(b + 1) * cpb] - p0;
+        const int nsp = (cnt + maxsub - 1) / maxsub;
+        binsize[b] = cnt; binstartpts[b] = p0; numsubprob[b] = nsp; subprobstartpts[b] = nsp;
+    } else if (b == nbins) subprobstartpts[b] = 0;
 }
 
 // internal bins (finer than the reference's): subproblem count per internal bin, to be scanned
@@ -302,19 +275,35 @@ __device__ __forceinline__ void store_rec<double>(PtRec<double> *dst, double xr,
     d[1] = make_double2(zr, __longlong_as_double((long long)i));
 }
 
-// K6: scatter one record per point to its sorted slot.
+// K6: scatter one record per point to its sorted slot (four points per thread and iteration:
+// coordinate and rank loads first, then the offset gathers, then the record stores).
 template <typename T, int DIM>
 __global__ void __launch_bounds__(256)
 place_points_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
                     const SortGeo g, const int *__restrict__ keyoff, const int *__restrict__ rank,
                     PtRec<T> *__restrict__ recs)
 {
-    for (long long ii = (long long)blockIdx.x * blockDim.x + threadIdx.x; ii < M; ii += (long long)gridDim.x * blockDim.x) {
-        int i = (int)ii;
-        T xr, yr = 0, zr = 0;
-        int k = point_key<T, DIM>(x, y, z, i, g, xr, yr, zr);
-        int pos = keyoff[k] + rank[i];
-        store_rec<T>(recs + pos, xr, yr, zr, i);
+    const long long span = (long long)blockDim.x * SP_UNROLL;
+    for (long long base = (long long)blockIdx.x * span; base < M; base += (long long)gridDim.x * span) {
+        T xr[SP_UNROLL], yr[SP_UNROLL], zr[SP_UNROLL];
+        int k[SP_UNROLL], rk[SP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SP_UNROLL; ++u) {
+            const long long i = base + (long long)u * blockDim.x + threadIdx.x;
+            xr[u] = 0; yr[u] = 0; zr[u] = 0; k[u] = 0; rk[u] = 0;
+            if (i < M) {
+                k[u] = point_key<T, DIM>(x, y, z, (int)i, g, xr[u], yr[u], zr[u]);
+                rk[u] = rank[i];
+            }
+        }
+        int pos[SP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SP_UNROLL; ++u) pos[u] = keyoff[k[u]] + rk[u];
+#pragma unroll
+        for (int u = 0; u < SP_UNROLL; ++u) {
+            const long long i = base + (long long)u * blockDim.x + threadIdx.x;
+            if (i < M) store_rec<T>(recs + pos[u], xr[u], yr[u], zr[u], (int)i);
+        }
     }
 }
 
@@ -339,6 +328,83 @@ extract_idx_kernel(int M, const PtRec<T> *__restrict__ recs, int *__restrict__ i
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x)
         idx[i] = rec_index(recs[i]);
+}
+
+// ---- second level of the two-level order -----------------------------------------------------
+// When the (bin, stencil cell) histogram gets much larger than L2 (config 5 on one GPU: 4.3 GB)
+// its random atomics and gathers run at DRAM-sector speed.  The global pass then sorts by
+// internal bin only (a table of a few MB: L2-resident) and this kernel orders every work item
+// (<= maxsub consecutive points of one bin) by stencil cell: records in registers (8 per thread),
+// cell histogram + ranks with shared-memory atomics, block scan, write back inside the item's own
+// range.  All global traffic of this pass is a coalesced read and a write confined to a 64 KB window.
+struct LocalSortArgs {
+    const int *keyoff, *s2b, *substart, *nsub;
+    int maxsub;
+    int nb1, nb2, rbs[3], ibs[3], spb1, spb2, spbt;
+    int ns, nkf[3], cpbf, zshift;
+};
+
+constexpr int LS_THREADS = 256;
+constexpr int LS_RPT = 8;                       // records per thread
+constexpr int LS_MAXKEYS = 4096;
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(LS_THREADS)
+local_sort_kernel(const LocalSortArgs a, PtRec<T> *__restrict__ recs)
+{
+    __shared__ int cnt[LS_MAXKEYS];
+    __shared__ int wsum[32];
+    const int nsub = *a.nsub;
+    for (int s = blockIdx.x; s < nsub; s += gridDim.x) {
+        const int bin = a.s2b[s];
+        const int k = s - a.substart[bin];
+        const int p0 = a.keyoff[bin], p1 = a.keyoff[bin + 1];
+        const int pstart = p0 + k * a.maxsub;
+        const int n = min(a.maxsub, p1 - pstart);
+        if (n < 2) continue;
+        const int rb = bin / a.spbt, sub = bin - rb * a.spbt;
+        const int b1 = rb % a.nb1, b23 = rb / a.nb1, s1 = sub % a.spb1, s23 = sub / a.spb1;
+        const int o1 = b1 * a.rbs[0] + s1 * a.ibs[0];
+        const int o2 = DIM > 1 ? (b23 % a.nb2) * a.rbs[1] + (s23 % a.spb2) * a.ibs[1] : 0;
+        const int o3 = DIM > 2 ? (b23 / a.nb2) * a.rbs[2] + (s23 / a.spb2) * a.ibs[2] : 0;
+        for (int c0 = 0; c0 < n; c0 += LS_THREADS * LS_RPT) {
+            const int m = min(LS_THREADS * LS_RPT, n - c0);
+            PtRec<T> *base = recs + pstart + c0;
+            for (int i = threadIdx.x; i < a.cpbf; i += LS_THREADS) cnt[i] = 0;
+            __syncthreads();
+            PtRec<T> r[LS_RPT];
+            int kr[LS_RPT];                                   // key << 13 | rank inside the key
+#pragma unroll
+            for (int j = 0; j < LS_RPT; ++j) {
+                const int i = j * LS_THREADS + threadIdx.x;
+                kr[j] = -1;
+                if (i < m) {
+                    r[j] = base[i];
+                    int key = a.nkf[0] > 1 ? stencil_cell(r[j].x, a.ns, o1, a.nkf[0]) : 0;
+                    if (DIM > 1 && a.nkf[1] > 1) key += a.nkf[0] * stencil_cell(r[j].y, a.ns, o2, a.nkf[1]);
+                    if (DIM > 2 && a.nkf[2] > 1) key += a.nkf[0] * a.nkf[1] * stencil_cell(r[j].z - (T)a.zshift, a.ns, o3, a.nkf[2]);
+                    kr[j] = (key << 13) | atomicAdd(&cnt[key], 1);       // (warp-aggregating this atomic was measured: slower)
+                }
+            }
+            __syncthreads();
+            // exclusive scan of cnt[0 .. cpbf): 16 entries per thread + block scan of the partial sums
+            {
+                constexpr int PER = LS_MAXKEYS / LS_THREADS;
+                int v[PER], sum = 0;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) { const int i = threadIdx.x * PER + j; v[j] = i < a.cpbf ? cnt[i] : 0; sum += v[j]; }
+                int total;
+                int run = block_exclusive_scan(sum, wsum, total);
+#pragma unroll
+                for (int j = 0; j < PER; ++j) { const int i = threadIdx.x * PER + j; if (i < a.cpbf) cnt[i] = run; run += v[j]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < LS_RPT; ++j)
+                if (kr[j] >= 0) base[cnt[kr[j] >> 13] + (kr[j] & 8191)] = r[j];
+            __syncthreads();
+        }
+    }
 }
 
 template <typename T, int DIM>
@@ -383,9 +449,18 @@ static int setpts_dim(Plan<T> &p)
     scan_reduce_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nscan, keyoff, tilesum);
     scan_top_kernel<<<1, 1024, 0, st>>>(ntiles, tilesum);
     scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nscan, keyoff, tilesum);
-    bins_from_keys_kernel<<<(p.nbins + 255) / 256, 256, 0, st>>>(p.nbins, g.cpb * g.spbt, keyoff, binsize);
-    scan_bins_kernel<<<1, 1024, 0, st>>>(p.nbins, p.opts.gpu_maxsubprobsize, binsize, binstart, nsub, substart, scal);
-    p.launches_setpts += 5;
+    {   // reference-facing arrays from the key offsets: binsize, binstartpts (= the offsets themselves),
+        // numsubprob (integer ceil), subprobstartpts by the same three-phase scan, total -> scalars[0]
+        const long long nrs = (long long)p.nbins + 1;
+        const int rtiles = (int)((nrs + SCAN_TILE - 1) / SCAN_TILE);
+        ref_bins_kernel<<<(int)((nrs + 255) / 256), 256, 0, st>>>(p.nbins, g.cpb * g.spbt, p.opts.gpu_maxsubprobsize, keyoff, binsize,
+                                                                 binstart, nsub, substart);
+        scan_reduce_kernel<<<rtiles, SCAN_THREADS, 0, st>>>(nrs, substart, tilesum);
+        scan_top_kernel<<<1, 1024, 0, st>>>(rtiles, tilesum);
+        scan_apply_kernel<<<rtiles, SCAN_THREADS, 0, st>>>(nrs, substart, tilesum);
+        CFB_CUDA_OK(cudaMemcpyAsync(scal, substart + p.nbins, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    }
+    p.launches_setpts += 7;
     int maxslots = p.nbins + M / p.opts.gpu_maxsubprobsize + 1;
     map_subprob_kernel<<<(maxslots + 255) / 256, 256, 0, st>>>(p.nbins, maxslots, substart, scal, s2b);
     p.launches_setpts++;
@@ -404,6 +479,20 @@ static int setpts_dim(Plan<T> &p)
     }
     if (M > 0) {
         place_points_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, g, keyoff, rank, recs);
+        p.launches_setpts++;
+    }
+    if (M > 0 && p.local_sort) {
+        LocalSortArgs la;
+        la.keyoff = keyoff;
+        la.s2b = p.ilist ? p.is2b.template as<int>() : s2b;
+        la.substart = p.ilist ? p.isubstart.template as<int>() : substart;
+        la.nsub = p.ilist ? p.isubstart.template as<int>() + p.nibins : scal;
+        la.maxsub = p.ilist ? p.imaxsub : p.opts.gpu_maxsubprobsize;
+        la.nb1 = p.nbin[0]; la.nb2 = p.nbin[1];
+        for (int d = 0; d < 3; ++d) { la.rbs[d] = p.bs[d]; la.ibs[d] = p.ibs[d]; la.nkf[d] = g.nkf[d]; }
+        la.spb1 = p.spb[0]; la.spb2 = p.spb[1]; la.spbt = g.spbt;
+        la.ns = p.ns; la.cpbf = g.cpbf; la.zshift = g.zshift;
+        local_sort_kernel<T, DIM><<<p.num_sms * 8, LS_THREADS, 0, st>>>(la, recs);
         p.launches_setpts++;
     }
     CFB_CUDA_OK(cudaGetLastError());
@@ -426,12 +515,22 @@ int stage_setpts(Plan<T> &p)
     for (int d = 0; d < 3; ++d) {
         g.nf[d] = nf[d]; g.bs[d] = p.bs[d]; g.nb[d] = p.nbin[d];
         g.ibs[d] = p.ibs[d]; g.spb[d] = p.spb[d];
-        g.nk[d] = d < p.dim ? p.ibs[d] + (p.ns & 1) : 1;
+        g.nk[d] = g.nkf[d] = d < p.dim ? p.ibs[d] + (p.ns & 1) : 1;
         cpb *= g.nk[d];
     }
     g.spbt = p.spb[0] * p.spb[1] * p.spb[2];
+    g.cpbf = (int)(cpb < (1LL << 30) ? cpb : (1LL << 30));
     long long nkeys = cpb * p.nibins;
-    if (!p.fine_sort_allowed || nkeys > 8LL * (long long)M + (1LL << 22) || nkeys > 2000000000LL) {
+    // one level (global (bin, cell) histogram) while that table is comfortably L2-sized and not much
+    // larger than the point set; two levels (bins globally, cells per work item) when it is not;
+    // bins only when a bin has more stencil cells than the local sort handles
+    const bool dense = nkeys <= 8LL * (long long)M + (1LL << 22);        // else runs have one point anyway: bins only
+    bool one_level = p.fine_sort_allowed && dense && nkeys * 4 <= (2048LL << 20);
+    bool two_level = p.fine_sort_allowed && dense && !one_level;
+    if (p.sort_levels == 2) { one_level = false; two_level = p.fine_sort_allowed; }
+    if (p.sort_levels == 1 && p.fine_sort_allowed && nkeys <= 2000000000LL) { one_level = true; two_level = false; }
+    p.local_sort = two_level && p.sorted && cpb <= LS_MAXKEYS;
+    if (!one_level) {
         g.nk[0] = g.nk[1] = g.nk[2] = 1;
         cpb = 1;
         nkeys = p.nibins;

@@ -163,6 +163,11 @@ class cufinufft:
         if self._fn["set_interp_engine"](self.plan, int(engine)) != 0:
             raise RuntimeError('Error selecting the interpolation engine.')
 
+    def set_sort_levels(self, levels):
+        """0 automatic, 1 one-level (bin, cell) histogram, 2 bins globally + cells per work item."""
+        if self._fn["set_sort_levels"](self.plan, int(levels)) != 0:
+            raise RuntimeError('Error selecting the sort mode.')
+
     def launch_counts(self):
         n = (c_int * 2)()
         self._fn["get_launch_counts"](self.plan, n)

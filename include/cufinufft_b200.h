@@ -100,6 +100,12 @@ int cufinufftf_get_timing(cufinufftf_plan plan, float *out);
  * (reference Interp_*_Subprob schedule).  Results agree to rounding; this is an A/B switch. */
 int cufinufft_set_interp_engine(cufinufft_plan plan, int engine);
 int cufinufftf_set_interp_engine(cufinufftf_plan plan, int engine);
+/* Order of the points inside a bin (takes effect at the next setpts): 0 = automatic, 1 = one level
+ * (global histogram over (bin, stencil cell) keys), 2 = two levels (bins globally, stencil cells per
+ * work item in shared memory -- chosen automatically when the one-level histogram would exceed 2 GB).
+ * Results do not depend on it; an A/B and test switch. */
+int cufinufft_set_sort_levels(cufinufft_plan plan, int levels);
+int cufinufftf_set_sort_levels(cufinufftf_plan plan, int levels);
 /* number of kernels this library launched in the last setpts / execute (bench.py's gpu_launches) */
 int cufinufft_get_launch_counts(cufinufft_plan plan, int *out2);
 int cufinufftf_get_launch_counts(cufinufftf_plan plan, int *out2);

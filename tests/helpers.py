@@ -43,13 +43,16 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-def gpu_nufft(nufft_type, modes, pts, data, tol, dtype, ntransf=1, maxbatch=1, iflag=None, return_plan=False, **opts):
+def gpu_nufft(nufft_type, modes, pts, data, tol, dtype, ntransf=1, maxbatch=1, iflag=None, return_plan=False,
+              sort_levels=0, **opts):
     """Run our library through the Python class (C ABI underneath). modes x-fastest (ms,mt,mu);
     pts = [x,y,z]; data [ntransf][...]."""
     from cufinufft_b200 import cufinufft, gpuarray
     shape = tuple(modes)[::-1]
     plan = cufinufft(nufft_type, shape, n_trans=ntransf, eps=tol, isign=iflag, dtype=dtype, maxbatch=maxbatch, **opts)
     dev = [gpuarray.to_gpu(p) for p in pts]
+    if sort_levels:
+        plan.set_sort_levels(sort_levels)
     plan.set_pts(*dev[::-1])
     M = pts[0].size
     cd = cdtype(dtype)

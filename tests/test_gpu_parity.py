@@ -116,7 +116,9 @@ def test_type1_with_internal_subbins(case):
     out, plan = gpu_nufft(1, modes, pts, data, tol, dtype, return_plan=True, **opts)
     ref = orc.nufft(1, modes, pts, data[0], tol, dtype=dtype)
     err = rel_l2(out[0], ref)
-    assert err <= TOL_PARITY[dtype], err
+    # every point in the same few cells: 6e4 fp32 additions per cell in an order that differs between
+    # the two implementations (and between runs of either): sqrt(N) * eps ~ 1.5e-5 is the noise floor
+    assert err <= TOL_PARITY[dtype] * (4 if dist == "onebin" else 1), err
     _check_bins(plan, pts, dtype, opts.get("gpu_maxsubprobsize", 1024))
     # a second setpts with few points on the same plan falls back to the reference's bins
     few = [p[:500].copy() for p in pts]
@@ -129,3 +131,34 @@ def test_type1_with_internal_subbins(case):
     ref2 = orc.nufft(1, modes, few, data[0, :500], tol, dtype=dtype)
     assert rel_l2(fkg.get()[0], ref2) <= TOL_PARITY[dtype]
     _check_bins(plan, few, dtype, opts.get("gpu_maxsubprobsize", 1024))
+
+
+# The two-level point order (bins globally, stencil cells per work item: csrc/setpts.cu
+# local_sort_kernel) is chosen automatically only for histograms beyond 2 GB; forced here on
+# small inputs of every kind.  Same results, same reference-facing bin arrays.
+TWO_LEVEL_CASES = [
+    (1, (128, 96), 400000, 1e-3, np.float32, "uniform", {}),
+    (1, (64, 64), 60000, 1e-4, np.float32, "onebin", {}),
+    (2, (64, 48), 50000, 1e-9, np.float64, "uniform", {}),
+    (1, (32, 32, 32), 300000, 1e-5, np.float32, "cluster", {}),
+    (2, (20, 18, 16), 100000, 1e-9, np.float64, "wide", {}),
+    (1, (24, 20, 16), 150000, 1e-6, np.float32, "cluster", dict(gpu_maxsubprobsize=3000)),
+    (1, (24, 20, 16), 50000, 1e-5, np.float32, "uniform", dict(gpu_method=1)),
+    (1, (300,), 100000, 1e-5, np.float32, "uniform", {}),
+]
+
+
+@pytest.mark.parametrize("case", TWO_LEVEL_CASES, ids=lambda c: "t%d-%s-M%d-%s-%s" % (c[0], "x".join(map(str, c[1])), c[2], np.dtype(c[4]).name, c[5]))
+def test_two_level_point_order(case):
+    nufft_type, modes, M, tol, dtype, dist, opts = case
+    dim = len(modes)
+    pts = make_points(M, dim, dtype, seed=91, dist=dist)
+    data = make_strengths(M, dtype) if nufft_type == 1 else make_modes_data(modes, dtype)
+    out, plan = gpu_nufft(nufft_type, modes, pts, data, tol, dtype, return_plan=True, sort_levels=2, **opts)
+    ref = orc.nufft(nufft_type, modes, pts, data[0], tol, dtype=dtype)
+    slack = 4 if dist == "onebin" else 1                 # fp32 accumulation-order noise, see above
+    assert rel_l2(out[0], ref) <= TOL_PARITY[dtype] * slack
+    one = gpu_nufft(nufft_type, modes, pts, data, tol, dtype, sort_levels=1, **opts)
+    assert rel_l2(out[0], one[0]) <= TOL_PARITY[dtype] * slack
+    _check_bins(plan, pts, dtype, opts.get("gpu_maxsubprobsize", 1024))
+    assert plan.launch_counts()["setpts"] >= 9          # the local sort ran
