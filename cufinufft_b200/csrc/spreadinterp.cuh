@@ -443,6 +443,7 @@ spread_sm_kernel(const SIArgs<T> a_in)
                     for (int j = 0; j < 8; ++j)
                         if (c0 + j < G::ITERS && active && (c0 + j) * G::R + r < G::ROWS) cell0[tile_off(c0 + j)] = v[j];
                 }
+                __syncwarp();      // the next point's loads (other lanes, possibly the same cells) come after these stores
             }
         };
 
