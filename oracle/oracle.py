@@ -196,14 +196,14 @@ def plan_params(nufft_type, modes, tol, dtype, gpu_method=None, kerevalmeth=0, u
     return kp, nf, bs[:dim], gpu_method
 
 
-def nufft(nufft_type, modes, pts, data, tol, iflag=None, dtype=np.float64, kerevalmeth=0):
+def nufft(nufft_type, modes, pts, data, tol, iflag=None, dtype=np.float64, kerevalmeth=0, upsampfac=2.0):
     """Full transform of ONE data vector through the oracle.
     modes = (ms[,mt[,mu]]) with x fastest; type 1: data=c[M] -> fk[mu][mt][ms];
     type 2: data=fk -> c[M].  Call stack: src/2d/cufinufft2d.cu:15-92 / :94-165."""
     dim = len(modes)
     if iflag is None:
         iflag = 1 if nufft_type == 1 else -1
-    kp, nf, _, _ = plan_params(nufft_type, modes, tol, dtype, kerevalmeth=kerevalmeth)
+    kp, nf, _, _ = plan_params(nufft_type, modes, tol, dtype, kerevalmeth=kerevalmeth, upsampfac=upsampfac)
     kers = [fwkerhalf(nf[d], kp) for d in range(dim)]
     cd = np.complex64 if np.dtype(dtype) == np.float32 else np.complex128
     fft = np.fft.ifftn if iflag >= 0 else np.fft.fftn      # cuFFT direction = iflag, unnormalised

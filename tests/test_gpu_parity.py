@@ -162,3 +162,33 @@ def test_two_level_point_order(case):
     assert rel_l2(out[0], one[0]) <= TOL_PARITY[dtype] * slack
     _check_bins(plan, pts, dtype, opts.get("gpu_maxsubprobsize", 1024))
     assert plan.launch_counts()["setpts"] >= 9          # the local sort ran
+
+
+# Nonstandard upsampling factors (opts.upsampfac != 2: kernel width and beta from the cutoff formulas of
+# contrib/spreadinterp.cpp:43-62, fine grid sigma * modes; direct kernel evaluation only).  The reference
+# accepts them through the same opts field; sigma = 1.25 shrinks the fine grid of a 3-D transform 4x.
+@pytest.mark.parametrize("case", [
+    (1, (60, 50), 30000, 1e-4, np.float32, 1.25), (2, (60, 50), 30000, 1e-4, np.float32, 1.25),
+    (1, (40, 36), 20000, 1e-8, np.float64, 1.5), (2, (20, 18, 16), 20000, 1e-6, np.float64, 1.25),
+    (1, (24, 20, 16), 20000, 1e-3, np.float32, 3.0),
+], ids=lambda c: "t%d-%s-%g-%s-sigma%g" % (c[0], "x".join(map(str, c[1])), c[3], np.dtype(c[4]).name, c[5]))
+def test_nonstandard_upsampfac(case):
+    nufft_type, modes, M, tol, dtype, sigma = case
+    dim = len(modes)
+    pts = make_points(M, dim, dtype, seed=12)
+    data = make_strengths(M, dtype) if nufft_type == 1 else make_modes_data(modes, dtype)
+    out, plan = gpu_nufft(nufft_type, modes, pts, data, tol, dtype, return_plan=True, upsampfac=sigma)
+    g = plan.geometry()
+    assert sigma * modes[0] - 1 <= g["nf1"] <= 1.2 * max(sigma * modes[0], 2 * g["ns"]) + 8      # next 2^a 3^b 5^c even above both
+    ref = orc.nufft(nufft_type, modes, pts, data[0], tol, dtype=dtype, upsampfac=sigma)
+    assert rel_l2(out[0], ref) <= TOL_PARITY[dtype]
+    rng = np.random.default_rng(5)
+    if nufft_type == 1:
+        idx = rng.integers(0, int(np.prod(modes)), 40)
+        exact, got = orc.dirft1_sampled(pts, data[0], modes, 1, idx), out[0].ravel()[idx]
+    else:
+        idx = rng.integers(0, M, 40)
+        exact, got = orc.dirft2_sampled(pts, data[0], modes, -1, idx), out[0][idx]
+    assert np.abs(got - exact).max() / np.abs(exact).max() <= max(20 * tol, 3e-6 if dtype == np.float32 else 1e-13)
+    with pytest.raises(RuntimeError):
+        gpu_nufft(nufft_type, modes, pts, data, tol, dtype, upsampfac=sigma, gpu_kerevalmeth=1)   # Horner needs sigma = 2

@@ -3,8 +3,8 @@
 TAG=${1:-thr}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-for thr in "" 1/1000 2/1 4/1 16/1 1000/1; do
-  for c in 1 3 4; do
+for thr in "" 2/1 3/1 4/1 6/1; do
+  for c in 1 4; do
     CFB_DIRECT_THR=$thr timeout 300 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/b.json 2> $OUT/b.err
     python - <<PY
 import json
