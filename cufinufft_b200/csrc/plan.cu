@@ -419,6 +419,23 @@ static int host_params(int type, int dim, const int *nmodes, double tol, const c
     return 0;
 }
 
+// what setpts would choose for M points, without a device: internal bins, tile, work-item size
+// (choose_internal_bins, spread.cu) -- for the host-logic tests
+template <typename T>
+static int host_workplan(int type, int dim, const int *nmodes, double tol, const cufinufft_opts *opts, long long M, int *o)
+{
+    Plan<T> p;
+    int ier = plan_host_setup<T>(&p, type, dim, nmodes, 1, 1, (T)tol, 1, opts);
+    if (ier) return ier;
+    p.M = (int)(M > 2147483647LL ? 2147483647LL : M);
+    plan_tile_geometry(p);
+    choose_internal_bins(p, M);
+    const int v[16] = {p.ibs[0], p.ibs[1], p.ibs[2], p.spb[0], p.spb[1], p.spb[2], p.nibins, p.nbins, p.imaxsub, p.ilist ? 1 : 0,
+                       p.tile_cells, p.tile_sy, p.tile_sz, p.sm_warps, p.tile_pad, p.tile_cost};
+    memcpy(o, v, sizeof(v));
+    return 0;
+}
+
 template <typename T>
 static int stage_only(Plan<T> *p, typename Plan<T>::C *c, typename Plan<T>::C *fw, int nt, bool spread)
 {
@@ -478,6 +495,13 @@ int cufinufft_b200_host_params(int type, int dim, const int *nmodes, double tol,
     if (!out_ints16 || !out_reals3) return CFB_ERR_BAD_ARG;
     return single_precision ? cfb::host_params<float>(type, dim, nmodes, tol, opts, out_ints16, out_reals3)
                             : cfb::host_params<double>(type, dim, nmodes, tol, opts, out_ints16, out_reals3);
+}
+int cufinufft_b200_host_workplan(int type, int dim, const int *nmodes, double tol, int single_precision,
+                                 const cufinufft_opts *opts, long long M, int *out_ints16)
+{
+    if (!out_ints16) return CFB_ERR_BAD_ARG;
+    return single_precision ? cfb::host_workplan<float>(type, dim, nmodes, tol, opts, M, out_ints16)
+                            : cfb::host_workplan<double>(type, dim, nmodes, tol, opts, M, out_ints16);
 }
 int cufinufft_b200_phihat_quadrature(int nf, int ns, double beta, double es_c, double halfwidth, int single_precision,
                                      void *f, double *a_reim)

@@ -51,6 +51,14 @@ int cufinufft_b200_host_params(int type, int dim, const int *nmodes, double tol,
                                const cufinufft_opts *opts, int *out_ints16, double *out_reals3);
 int cufinufft_b200_phihat_quadrature(int nf, int ns, double beta, double es_c, double halfwidth, int single_precision,
                                      void *f, double *a_reim);
+/*  host_workplan: what setpts would choose for M points on a B200 (148 SMs, 227 KB shared memory) --
+ *    out_ints16 = {ibinsx, ibinsy, ibinsz (internal bin = reference bin / sub-bins per bin), sub-bins per
+ *                  reference bin x, y, z, #internal bins, #reference bins, points per work item, own work
+ *                  list (0|1), tile cells, tile stride y, tile stride z, warps per SM-spread block,
+ *                  halo ceil(ns/2), bank-conflict cost of the tile layout}
+ *    (no reference counterpart: the reference's work items are its bins, src/2d/spread2d_wrapper.cu:386-613). */
+int cufinufft_b200_host_workplan(int type, int dim, const int *nmodes, double tol, int single_precision,
+                                 const cufinufft_opts *opts, long long M, int *out_ints16);
 
 /* Stream on which all work of the plan is enqueued (default: the legacy default stream 0).
  * `stream` is a cudaStream_t passed as void*. */

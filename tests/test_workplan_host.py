@@ -1,0 +1,107 @@
+"""Host-only tests of the work plan `setpts` derives for the tile engines (csrc/spread.cu:
+choose_internal_bins, plan_tile_geometry) through cufinufft_b200_host_workplan -- no device needed.
+Invariants: sub-bins tile the reference's bins exactly (the reference-facing arrays are sums over
+them), tiles fit the shared memory of a B200 SM, dense inputs get smaller tiles / larger work items,
+sparse ones keep the reference's bins, type 2 plans are never split."""
+from ctypes import c_int
+
+import numpy as np
+import pytest
+
+KEYS = ("ibsx", "ibsy", "ibsz", "spbx", "spby", "spbz", "nibins", "nbins", "imaxsub", "ilist", "tile_cells", "tile_sy",
+        "tile_sz", "sm_warps", "pad", "tile_cost")
+
+
+def workplan(nufft_type, modes, tol, dtype, M, **opts):
+    from cufinufft_b200 import _cufinufft as ll
+    o = ll.NufftOpts()
+    assert ll._default_opts(nufft_type, len(modes), o) == 0
+    for k, v in opts.items():
+        setattr(o, k, v)
+    m = (c_int * 3)(*(tuple(modes) + (1,) * (3 - len(modes))))
+    out = (c_int * 16)()
+    ier = ll.host_workplan(nufft_type, len(modes), m, tol, int(np.dtype(dtype) == np.float32), o, int(M), out)
+    assert ier == 0
+    return dict(zip(KEYS, list(out)))
+
+
+def _ref_bins(nufft_type, modes, dtype, opts):
+    dim = len(modes)
+    if dim == 1:
+        d = [1024, 1, 1]
+    elif dim == 2:
+        d = [32, 32, 1]
+    else:
+        d = [16, 16, 2]
+    for k, i in (("gpu_binsizex", 0), ("gpu_binsizey", 1), ("gpu_binsizez", 2)):
+        if opts.get(k, -1) > 0 and i < dim:
+            d[i] = opts[k]
+    return d
+
+
+CONFIGS = [
+    # (type, modes, tol, dtype, M, opts)                                 BASELINE.json configs 1, 3, 4 and friends
+    (1, (1000, 1000), 1e-3, np.float32, 10_000_000, {}),
+    (1, (256, 256, 256), 1e-5, np.float32, 100_000_000, {}),
+    (1, (512, 512), 1e-4, np.float32, 262_144, {}),
+    (1, (512, 512, 512), 1e-9, np.float64, 1_000_000_000, {}),
+    (1, (100, 80), 1e-6, np.float32, 300_000, dict(gpu_binsizex=24, gpu_binsizey=10)),
+    (1, (64, 64, 64), 1e-12, np.float64, 5_000_000, {}),
+    (1, (64, 48), 1e-4, np.float32, 100, {}),
+    (1, (3000,), 1e-5, np.float32, 1_000_000, {}),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: "t%d-%s-M%d-%s" % (c[0], "x".join(map(str, c[1])), c[4], np.dtype(c[3]).name))
+def test_workplan_invariants(cfg):
+    nufft_type, modes, tol, dtype, M, opts = cfg
+    dim = len(modes)
+    w = workplan(nufft_type, modes, tol, dtype, M, **opts)
+    bs = _ref_bins(nufft_type, modes, dtype, opts)
+    ibs, spb = [w["ibsx"], w["ibsy"], w["ibsz"]], [w["spbx"], w["spby"], w["spbz"]]
+    for d in range(3):
+        assert ibs[d] * spb[d] == bs[d], (d, ibs, spb, bs)                # sub-bins tile the reference bin exactly
+        assert spb[d] & (spb[d] - 1) == 0                                  # by repeated halving
+    assert w["nibins"] == w["nbins"] * spb[0] * spb[1] * spb[2]
+    assert w["ilist"] == int(w["nibins"] != w["nbins"] or w["imaxsub"] != opts.get("gpu_maxsubprobsize", 1024))
+    assert w["imaxsub"] >= opts.get("gpu_maxsubprobsize", 1024) and w["imaxsub"] <= max(4096, opts.get("gpu_maxsubprobsize", 1024))
+    # the tile covers the internal bin + halo on every side, with padded strides
+    ex, ey, ez = ibs[0] + 2 * w["pad"], (ibs[1] + 2 * w["pad"]) if dim > 1 else 1, (ibs[2] + 2 * w["pad"]) if dim > 2 else 1
+    assert w["tile_sy"] >= ex
+    if dim == 3:
+        assert w["tile_sz"] >= w["tile_sy"] * ey
+    assert w["tile_cells"] >= ex * ey * ez
+    cell_bytes = 8 if dtype == np.float32 else 16
+    if w["sm_warps"] > 0:
+        assert w["sm_warps"] * w["tile_cells"] * cell_bytes <= 227 * 1024
+    if dim == 1:
+        assert w["nibins"] == w["nbins"]                                   # 1-D is never split
+
+
+def test_dense_inputs_get_more_resident_warps():
+    # config 3: the reference's 22x22x8 tile allows 5 warps per SM; the split must at least double that
+    w = workplan(1, (256, 256, 256), 1e-5, np.float32, 100_000_000)
+    per_warp = w["tile_cells"] * 8
+    assert w["nibins"] > w["nbins"] and per_warp <= 16 * 1024
+    assert w["ibsx"] == 16                                                 # x keeps the conflict-free stride of 22 cells
+    assert w["imaxsub"] == 100_000_000 // (16 * 148 * 16)                 # larger work items (one tile flush each), >= 16 per resident warp
+    # config 1: split once or twice, still >= 64 points per sub-bin
+    w1 = workplan(1, (1000, 1000), 1e-3, np.float32, 10_000_000)
+    assert w1["nibins"] > w1["nbins"] and 10_000_000 >= 64 * w1["nibins"]
+
+
+def test_sparse_inputs_and_type2_keep_the_reference_bins():
+    w = workplan(1, (256, 256, 256), 1e-5, np.float32, 100_000)           # 0.4 points per bin
+    assert w["nibins"] == w["nbins"] and w["ilist"] == 0
+    w = workplan(2, (2048, 2048), 1e-9, np.float64, 40_000_000, gpu_method=1)
+    assert w["nibins"] == w["nbins"] and w["ilist"] == 0 and w["imaxsub"] == 1024
+    w = workplan(1, (1000, 1000), 1e-3, np.float32, 10_000_000, gpu_method=1)   # GM engine: no tiles, no split
+    assert w["nibins"] == w["nbins"] and w["ilist"] == 0
+
+
+def test_wide_fp64_stencils_are_split_until_four_warps_fit():
+    # 3-D fp64 ns = 10: the reference's bin needs a 130 KB tile (one warp per SM); the split goes on
+    # regardless of density while fewer than four warps fit
+    w = workplan(1, (512, 512, 512), 1e-9, np.float64, 1_000_000)
+    assert w["nibins"] > w["nbins"]
+    assert w["sm_warps"] >= 3 or min(w["ibsx"], w["ibsy"]) <= 4
