@@ -85,9 +85,13 @@ def test_dense_inputs_get_more_resident_warps():
     assert w["nibins"] > w["nbins"] and per_warp <= 16 * 1024
     assert w["ibsx"] == 16                                                 # x keeps the conflict-free stride of 22 cells
     assert w["imaxsub"] == 100_000_000 // (16 * 148 * 16)                 # larger work items (one tile flush each), >= 16 per resident warp
-    # config 1: split once or twice, still >= 64 points per sub-bin
+    # config 1: the 36x36 tile + the single-pass scratch already fit the 14 KB per-warp target; never
+    # fewer than 64 points per (sub-)bin
     w1 = workplan(1, (1000, 1000), 1e-3, np.float32, 10_000_000)
-    assert w1["nibins"] > w1["nbins"] and 10_000_000 >= 64 * w1["nibins"]
+    assert w1["tile_cells"] * 8 <= 14 * 1024 and 10_000_000 >= 64 * w1["nibins"]
+    # config 4 (ns = 5: 38x38 tile): same
+    w4 = workplan(1, (512, 512), 1e-4, np.float32, 262_144)
+    assert w4["tile_cells"] * 8 <= 14 * 1024 and 262_144 >= 64 * w4["nibins"]
 
 
 def test_sparse_inputs_and_type2_keep_the_reference_bins():
