@@ -86,7 +86,7 @@ __device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__res
 // one atomicAdd (clustered inputs put most of a warp on one key).
 // Four points per thread and iteration: the twelve coordinate loads are in flight together, then the
 // four histogram atomics, then the four rank stores (one point per iteration left the kernel at the
-// latency of load -> atomic -> store chains: 1.7 TB/s with every table L2-resident, profiles/r02i).
+// latency of load -> atomic -> store chains: 1.7 TB/s with every table L2-resident, profiles/r01zi).
 constexpr int SP_UNROLL = 4;
 
 template <typename T, int DIM>

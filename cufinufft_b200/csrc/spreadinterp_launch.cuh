@@ -92,7 +92,7 @@ static int do_interp_tile(Plan<T> &p, SIArgs<T> &a, bool &done)
     // about one point per 64 tile cells (3-D fp64 ns=10: 127 points per bin, 2-D fp32 ns=4: 20).
     // The gather engine lives on L2 reuse between neighbouring bins, though: in 3-D it needs the ns
     // planes a stencil spans to stay resident (config 5's 1024^2 x 10 planes = 168 MB do not: measured
-    // 6.1 ns/point gather vs 3.4 tile at 60 points per bin, profiles/r02c), else the tile engine stays.
+    // 6.1 ns/point gather vs 3.4 tile at 60 points per bin, profiles/r01zc), else the tile engine stays.
     const bool sparse = (unsigned long long)p.M * 64ull < (unsigned long long)p.nbins * cells;
     const bool planes_fit_l2 = DIM < 3 || (long long)NS * p.nf1 * p.nf2 * (long long)sizeof(C) <= p.l2_bytes / 2;
     if (p.interp_engine == 0 && sparse && planes_fit_l2) return 0;
