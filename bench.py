@@ -260,7 +260,8 @@ def run_reference_impl(args, cfg, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * cfg["M"] * cfg["ntransf"] / res["value"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if cfg["dtype"] == "float32" else "f64", "data": "synthetic",
-        "config": {"workload": cfg["name"]},
+        "config": {"workload": cfg["name"], "type": cfg["type"], "modes": list(cfg["modes"]), "M_per_gpu": cfg["M"],
+                   "ntransf_per_gpu": cfg["ntransf"], "tol": cfg["tol"]},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "NU pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
