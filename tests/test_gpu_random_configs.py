@@ -70,8 +70,13 @@ def test_random_plan_matches_oracle(seed):
         ref = orc.nufft(d["type"], modes, pts, data[t], d["tol"], iflag=d["iflag"], dtype=dtype, kerevalmeth=kem)
         err = rel_l2(out[t], ref)
         scale = max(scale, float(np.abs(ref).max()))
-        # one- and two-point inputs: the result can be tiny where the kernel tails cancel; rel-l2 is still meaningful
-        assert err <= 4 * TOL_PARITY[dtype], (d, t, err)
+        # one- and two-point inputs: the result can be tiny where the kernel tails cancel; rel-l2 is still meaningful.
+        # all points in a few cells ("onebin"): the summation order of M additions per cell differs between the two
+        # implementations (and between runs: atomics), noise floor ~ sqrt(M) * eps
+        bound = 4 * TOL_PARITY[dtype]
+        if d["dist"] == "onebin":
+            bound = max(bound, 3 * np.sqrt(M) * np.finfo(dtype).eps)
+        assert err <= bound, (d, t, err)
     assert np.all(np.isfinite(np.asarray(out).view(np.float32 if dtype == np.float32 else np.float64)))
     g = plan.geometry()
     if g["method"] == 2 or d["opts"].get("gpu_sort", 1):
