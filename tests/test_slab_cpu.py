@@ -1,7 +1,7 @@
 """CPU tests of the z-slab decomposition of one 3-D transform: the
 orchestration code of cufinufft_b200.multi (ring halo exchange, all-reduce of the partial mode
 arrays, routing of points to their slabs) runs here on CPU tensors -- in one process with all
-ranks emulated, and under torch.distributed (gloo, world_size 2) -- with the oracle-backed
+ranks emulated, and under torch.distributed (gloo, world_size 2 and 3) -- with the oracle-backed
 slab stages of tests/slab_oracle.py standing in for the CUDA ones.  The result must equal the
 undivided oracle transform."""
 import os
@@ -127,10 +127,11 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_slab_pipeline_gloo_world2(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])      # 2: both neighbours are the same peer; 3: the general ring
+def test_slab_pipeline_gloo(tmp_path, world):
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     modes, M, tol, dtype = (12, 10, 16), 4000, 1e-9, np.float64
     pts = make_points(M, 3, dtype, seed=33, dist="wide")
     c = make_strengths(M, dtype)[0]
