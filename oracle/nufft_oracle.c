@@ -96,10 +96,10 @@ void orc_default_binsize(int dim, int gpu_method, int *bs /*3*/, int *obs /*3*/)
     }
 }
 
-/* ---- Horner tables (our generator's output, shared with the product as DATA) */
-#include "../cufinufft_b200/csrc/horner_coeffs.inc"
-static const double *orc_horner_table(int w) { return cfb_horner_coeffs[w]; }
-static int orc_horner_ncoef(int w) { return cfb_horner_ncoef[w]; }
+/* ---- Horner tables: the reference's generated constants, contrib/ker_horner_allw_loop.c:4-216 */
+#include "horner_ref_table.inc"   /* the oracle's OWN copy of the reference table (tools/import_horner_table.py) */
+static const double *orc_horner_table(int w) { return orcref_horner_coeffs[w]; }
+static int orc_horner_ncoef(int w) { return orcref_horner_ncoef[w]; }
 const double *orc_horner_table_export(int w) { return orc_horner_table(w); }
 int orc_horner_ncoef_export(int w) { return orc_horner_ncoef(w); }
 

@@ -200,9 +200,9 @@ static inline void ORC(kervec)(FLT *ker, FLT x1, int ns, FLT es_c, FLT es_beta)
         ker[i] = ORC(dev_kernel)((FLT)fabs((double)(x1 + (FLT)i)), es_c, es_beta, ns);
 }
 
-/* eval_kernel_vec_Horner: src/cuspreadinterp.h:18-31, tables from our own
- * generator (cufinufft_b200/csrc/horner_coeffs.inc; the reference's table is
- * contrib/ker_horner_allw_loop.c).  z = 2x + w - 1.0 is double then FLT. */
+/* eval_kernel_vec_Horner: src/cuspreadinterp.h:18-31 with the reference's table
+ * (contrib/ker_horner_allw_loop.c:4-216, imported into oracle/horner_ref_table.inc).
+ * z = 2x + w - 1.0 is double then FLT. */
 static inline void ORC(kervec_horner)(FLT *ker, FLT x, int w)
 {
     FLT zz = (FLT)(2 * (double)x + w - 1.0);
