@@ -109,7 +109,7 @@ struct Plan {
     int horner_ncoef = 0;
     cufftHandle fftplan = 0;
     bool have_fft = false;
-    cudaStream_t stream = 0;
+    cudaStream_t stream = cudaStreamPerThread;   // the reference is built with --default-stream per-thread (Makefile:35)
     int device = 0;
     int num_sms = 148;
     int max_smem_optin = 227 * 1024;

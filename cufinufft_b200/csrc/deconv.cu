@@ -50,10 +50,11 @@ int stage_fseries(Plan<T> &p)
     const int nf[3] = {p.nf1, p.nf2, nf3};
     for (int d = 0; d < p.dim; ++d)
         fseries_precomp<T>(nf[d], p.ns, p.es_beta, p.es_c, p.es_halfwidth, f + d * MAX_NQUAD, a + 2 * d * MAX_NQUAD);
-    T *d_f = nullptr;
-    double *d_a = nullptr;
-    CFB_CUDA_OK(cudaMalloc(&d_f, sizeof(f)));
-    CFB_CUDA_OK(cudaMalloc(&d_a, sizeof(a)));
+    struct Scoped : DevBuf { ~Scoped() { release(); } } bf, ba;      // freed on every return path
+    CFB_CUDA_OK(bf.reserve(sizeof(f)));
+    CFB_CUDA_OK(ba.reserve(sizeof(a)));
+    T *d_f = bf.template as<T>();
+    double *d_a = ba.template as<double>();
     CFB_CUDA_OK(cudaMemcpyAsync(d_f, f, sizeof(f), cudaMemcpyHostToDevice, p.stream));
     CFB_CUDA_OK(cudaMemcpyAsync(d_a, a, sizeof(a), cudaMemcpyHostToDevice, p.stream));
     const int q = (int)(2 + 3.0 * (T)(p.ns / 2.0));
@@ -63,8 +64,6 @@ int stage_fseries(Plan<T> &p)
                                                   p.fwker[1].template as<T>(), p.fwker[2].template as<T>());
     CFB_CUDA_OK(cudaGetLastError());
     CFB_CUDA_OK(cudaStreamSynchronize(p.stream));   // f/a are stack + temporaries: plan time only
-    cudaFree(d_f);
-    cudaFree(d_a);
     return 0;
 }
 

@@ -23,7 +23,11 @@ struct DeviceGuard {            // every API call runs on opts.gpu_device_id and
         cudaGetDevice(&prev);
         if (dev != prev) cudaSetDevice(dev);
         target = dev;
-        cudaGetLastError();     // do not inherit a stale non-sticky error left by other code in the process
+        // A stale non-sticky error left by other CUDA code in the process would be reported by our own
+        // post-launch checks as ours: take it off the error slot, but say so instead of hiding it.
+        const cudaError_t stale = cudaGetLastError();
+        if (stale != cudaSuccess)
+            fprintf(stderr, "[cufinufft-b200] note: a CUDA error was already pending on entry (not ours): %s\n", cudaGetErrorString(stale));
     }
     ~DeviceGuard() { if (target != prev) cudaSetDevice(prev); }
     int target = 0;
@@ -326,15 +330,16 @@ static int execute_host(Plan<T> *p, typename Plan<T>::C *c, typename Plan<T>::C 
     using C = typename Plan<T>::C;
     if (!p || p->M < 0) return CFB_ERR_BAD_ARG;
     DeviceGuard guard(p->device);
-    const size_t nc = (size_t)p->ntransf * (size_t)(p->M > 0 ? p->M : 1) * sizeof(C);
+    const size_t nc = (size_t)p->ntransf * (size_t)p->M * sizeof(C);      // M == 0: nothing of c is read or written
     const size_t nk = (size_t)p->ntransf * (p->opts.gpu_spreadinterponly ? p->grid_cells() : p->nmodes()) * sizeof(C);
-    CFB_CUDA_OK(dc.reserve(nc));
+    if ((nc && !c) || !fk) return CFB_ERR_BAD_ARG;
+    CFB_CUDA_OK(dc.reserve(nc ? nc : sizeof(C)));
     CFB_CUDA_OK(dfk.reserve(nk));
-    if (p->type == 1) CFB_CUDA_OK(cudaMemcpyAsync(dc.p, c, nc, cudaMemcpyHostToDevice, p->stream));
+    if (p->type == 1) { if (nc) CFB_CUDA_OK(cudaMemcpyAsync(dc.p, c, nc, cudaMemcpyHostToDevice, p->stream)); }
     else CFB_CUDA_OK(cudaMemcpyAsync(dfk.p, fk, nk, cudaMemcpyHostToDevice, p->stream));
     if (int e = execute(p, dc.as<C>(), dfk.as<C>())) return e;
     if (p->type == 1) CFB_CUDA_OK(cudaMemcpyAsync(fk, dfk.p, nk, cudaMemcpyDeviceToHost, p->stream));
-    else CFB_CUDA_OK(cudaMemcpyAsync(c, dc.p, nc, cudaMemcpyDeviceToHost, p->stream));
+    else if (nc) CFB_CUDA_OK(cudaMemcpyAsync(c, dc.p, nc, cudaMemcpyDeviceToHost, p->stream));
     CFB_CUDA_OK(cudaStreamSynchronize(p->stream));
     return 0;
 }

@@ -89,7 +89,7 @@ template <typename T, int DIM, int NS> struct Geo {
     static constexpr int KP = VEC ? (((KP0 / V) | 1) * V) : (KP0 | 1);
     static constexpr int NACC = VEC ? WS : (DIM == 1 ? 1 : roundup(ITERS, 2));   // accumulator slots (padded passes have weight 0)
     static constexpr bool MERGE = NACC * (int)(sizeof(T) / 4) <= 48;      // run accumulators (4 NACC 32-bit registers in fp64) fit in registers
-    static constexpr bool TOFF_REGS = sizeof(T) == 4 || ITERS <= 16;      // per-pass tile offsets kept in registers
+    static constexpr bool TOFF_REGS = ITERS <= (sizeof(T) == 4 ? 32 : 16);  // per-pass tile offsets kept in registers
     static constexpr int SM_MAXW = ITERS * (int)(sizeof(T) / 4) > 24 ? 4 : 16;   // warps per SM-spread block (register budget)
 };
 

@@ -37,11 +37,10 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     a.horner = p.opts.gpu_kerevalmeth == 1; a.ncoef = p.horner_ncoef;
     a.es_c = p.es_c; a.es_beta = p.es_beta;
     a.zshift = p.slab ? p.zshift : 0;
-    a.thr_num = 0; a.thr_den = 1;
-    if (const char *e = getenv("CFB_DIRECT_THR")) {         // experiments only: "num/den" = run length below which a batch goes point by point
-        int n = 0, d = 1;
-        if (sscanf(e, "%d/%d", &n, &d) >= 1 && n > 0 && d > 0) { a.thr_num = n; a.thr_den = d; }
-    }
+    // experiments only (read once per process): CFB_DIRECT_THR="num/den" = run length below which a batch goes point by point
+    static const struct Thr { int n = 0, d = 1; Thr() { if (const char *e = getenv("CFB_DIRECT_THR")) { int a_ = 0, b_ = 1;
+                          if (sscanf(e, "%d/%d", &a_, &b_) >= 1 && a_ > 0 && b_ > 0) { n = a_; d = b_; } } } } thr;
+    a.thr_num = thr.n; a.thr_den = thr.d;
     a.fwstride = (long long)p.grid_cells();
     return a;
 }
@@ -141,7 +140,7 @@ static int do_interp(Plan<T> &p, SIArgs<T> &a)
 }
 
 template <typename T> struct max_ns;
-template <> struct max_ns<float>  { static constexpr int v = 9; };   // tol clamps at 6e-8 -> ns <= 9
+template <> struct max_ns<float>  { static constexpr int v = 16; };  // upsampfac 2 clamps at ns = 9, other upsampling factors do not (sigma 1.25, tol 1e-6: ns = 10)
 template <> struct max_ns<double> { static constexpr int v = 16; };
 
 // development builds (make EXTRA=-DCFB_DEV_NS) instantiate only the widths of the five

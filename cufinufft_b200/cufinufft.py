@@ -107,6 +107,25 @@ class cufinufft:
         if self._fn["set_stream"](self.plan, c_void_p(int(stream_handle))) != 0:
             raise RuntimeError('Error setting stream.')
 
+    def set_pts_host(self, kx, ky=None, kz=None):
+        """set_pts with HOST numpy arrays (cufinufft[f]_setpts_host): copied to a plan-owned device buffer."""
+        given = [np.ascontiguousarray(a, self.dtype) for a in (kx, ky, kz) if a is not None]
+        M = given[0].size
+        if any(a.size != M for a in given):
+            raise TypeError("Number of elements in kx, ky, kz must be equal")
+        self.references = list(given)
+        ptrs = [a.ctypes.data for a in reversed(given)] + [None] * (3 - len(given))
+        if self._fn["set_pts_host"](M, ptrs[0], ptrs[1], ptrs[2], self.plan) != 0:
+            raise RuntimeError('Error setting non-uniform points.')
+        self.M = M
+
+    def execute_host(self, c, fk):
+        """execute with HOST numpy arrays (cufinufft[f]_execute_host); returns when the result is in host memory."""
+        if not (c.dtype == fk.dtype == self.complex_dtype and c.flags.c_contiguous and fk.flags.c_contiguous):
+            raise TypeError("cufinufft execute_host expects contiguous {} arrays.".format(self.complex_dtype))
+        if self._fn["exec_host"](c.ctypes.data, fk.ctypes.data, self.plan) != 0:
+            raise RuntimeError('Error executing plan.')
+
     def spread(self, c, fw, n_trans=1):
         if self._fn["spread"](c.ptr, fw.ptr, n_trans, self.plan) != 0:
             raise RuntimeError('Error spreading.')

@@ -60,7 +60,8 @@ int cufinufft_b200_phihat_quadrature(int nf, int ns, double beta, double es_c, d
 int cufinufft_b200_host_workplan(int type, int dim, const int *nmodes, double tol, int single_precision,
                                  const cufinufft_opts *opts, long long M, int *out_ints16);
 
-/* Stream on which all work of the plan is enqueued (default: the legacy default stream 0).
+/* Stream on which all work of the plan is enqueued (default: the calling thread's per-thread default
+ * stream, cudaStreamPerThread, as in the reference build).
  * `stream` is a cudaStream_t passed as void*. */
 int cufinufft_set_stream(cufinufft_plan plan, void *stream);
 int cufinufftf_set_stream(cufinufftf_plan plan, void *stream);

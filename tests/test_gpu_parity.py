@@ -171,6 +171,9 @@ def test_two_level_point_order(case):
     (1, (60, 50), 30000, 1e-4, np.float32, 1.25), (2, (60, 50), 30000, 1e-4, np.float32, 1.25),
     (1, (40, 36), 20000, 1e-8, np.float64, 1.5), (2, (20, 18, 16), 20000, 1e-6, np.float64, 1.25),
     (1, (24, 20, 16), 20000, 1e-3, np.float32, 3.0),
+    # single precision with kernels wider than upsampfac 2 ever needs (ns = 10, 13, 12):
+    (1, (64, 48), 20000, 1e-6, np.float32, 1.25), (2, (64, 48), 20000, 3e-7, np.float32, 1.25),
+    (1, (16, 14, 12), 5000, 1e-6, np.float32, 1.3), (2, (300,), 5000, 1e-6, np.float32, 1.25),
 ], ids=lambda c: "t%d-%s-%g-%s-sigma%g" % (c[0], "x".join(map(str, c[1])), c[3], np.dtype(c[4]).name, c[5]))
 def test_nonstandard_upsampfac(case):
     nufft_type, modes, M, tol, dtype, sigma = case

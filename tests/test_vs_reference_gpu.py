@@ -31,6 +31,15 @@ CASES = [
     (1, (64, 48), 20000, 1e-4, np.float32, "uniform", dict(gpu_method=2, gpu_kerevalmeth=1)),
     (2, (64, 48), 20000, 1e-4, np.float32, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),
     (1, (24, 20, 16), 20000, 1e-5, np.float32, "uniform", dict(gpu_method=2, gpu_kerevalmeth=1)),
+    # fp64 Horner (gpu_kerevalmeth=1) with the reference's own coefficient table: w = 5, 7, 10, 13 (VERDICT r1 "weak 2")
+    (1, (64, 48), 20000, 1e-4, np.float64, "uniform", dict(gpu_method=2, gpu_kerevalmeth=1)),
+    (2, (64, 48), 20000, 1e-6, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),
+    (1, (64, 48), 20000, 1e-9, np.float64, "cluster", dict(gpu_method=2, gpu_kerevalmeth=1)),
+    (2, (64, 48), 20000, 1e-12, np.float64, "uniform", dict(gpu_method=2, gpu_kerevalmeth=1)),
+    (1, (24, 20, 16), 20000, 1e-6, np.float64, "uniform", dict(gpu_method=2, gpu_kerevalmeth=1)),
+    (2, (24, 20, 16), 20000, 1e-9, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),
+    (1, (24, 20, 16), 20000, 1e-2, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),     # w = 3
+    (2, (500,), 20000, 1e-1, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),           # w = 2
 ]
 
 
