@@ -167,8 +167,12 @@ def _run_config(cfg_id, M=None, opts=None, check_bins=True, nsample=128):
     scale = float(exact.abs().max().item())
     e_ours = float((mine.to(torch.complex128) - exact).abs().max().item()) / scale
     e_ref = float((theirs.to(torch.complex128) - exact).abs().max().item()) / scale
-    print("config %d M=%d: rel-l2 vs reference %.3e; max err vs direct sum / max|exact|: ours %.3e, reference %.3e (tol %g)"
-          % (cfg_id, M, err, e_ours, e_ref, cfg["tol"]))
+    msg = ("config %d M=%d: rel-l2 vs reference %.3e; max err vs direct sum / max|exact|: ours %.3e, reference %.3e (tol %g)"
+           % (cfg_id, M, err, e_ours, e_ref, cfg["tol"]))
+    print(msg)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)       # scratch record of the measured numbers
+    with open(os.path.join(ROOT, "gpurun_out", "fullsize_parity.log"), "a") as fh:
+        fh.write(msg + "\n")
     del got, want, data, pts, parr
     gc.collect()
     torch.cuda.empty_cache()

@@ -184,14 +184,21 @@ def test_nonstandard_upsampfac(case):
     g = plan.geometry()
     assert sigma * modes[0] - 1 <= g["nf1"] <= 1.2 * max(sigma * modes[0], 2 * g["ns"]) + 8      # next 2^a 3^b 5^c even above both
     ref = orc.nufft(nufft_type, modes, pts, data[0], tol, dtype=dtype, upsampfac=sigma)
-    assert rel_l2(out[0], ref) <= TOL_PARITY[dtype]
     rng = np.random.default_rng(5)
     if nufft_type == 1:
         idx = rng.integers(0, int(np.prod(modes)), 40)
-        exact, got = orc.dirft1_sampled(pts, data[0], modes, 1, idx), out[0].ravel()[idx]
+        exact, got, want = orc.dirft1_sampled(pts, data[0], modes, 1, idx), out[0].ravel()[idx], ref.ravel()[idx]
     else:
         idx = rng.integers(0, M, 40)
-        exact, got = orc.dirft2_sampled(pts, data[0], modes, -1, idx), out[0][idx]
-    assert np.abs(got - exact).max() / np.abs(exact).max() <= max(20 * tol, 3e-6 if dtype == np.float32 else 1e-13)
+        exact, got, want = orc.dirft2_sampled(pts, data[0], modes, -1, idx), out[0][idx], ref[idx]
+    scale = np.abs(exact).max()
+    e_ours, e_ref = np.abs(got - exact).max() / scale, np.abs(want - exact).max() / scale
+    # Single precision with a low upsampling factor: the deconvolution divides by a phihat that spans ~1/tol, so the
+    # fp32 rounding of the fine grid is amplified far above tol in BOTH implementations (measured: the reference
+    # arithmetic itself is 1e-4 off the direct sum at sigma = 1.25, tol = 1e-6).  There the gate is "not worse than
+    # the reference arithmetic", and parity is measured against that noise level instead of 1e-5.
+    noisy = dtype == np.float32 and e_ref > 20 * tol
+    assert rel_l2(out[0], ref) <= (max(TOL_PARITY[dtype], 2 * e_ref) if noisy else TOL_PARITY[dtype])
+    assert e_ours <= max(20 * tol, 3e-6 if dtype == np.float32 else 1e-13, 2 * e_ref if noisy else 0.0)
     with pytest.raises(RuntimeError):
         gpu_nufft(nufft_type, modes, pts, data, tol, dtype, upsampfac=sigma, gpu_kerevalmeth=1)   # Horner needs sigma = 2

@@ -32,7 +32,8 @@ STAGE_CASES = [
     ((48, 40, 36), 300_000, 1e-5, np.float32, "cluster", dict(gpu_method=2)),
     ((48, 40, 36), 300_000, 1e-5, np.float32, "uniform", dict(gpu_method=1)),
     ((48, 40, 36), 300_000, 1e-4, np.float32, "uniform", dict(gpu_method=2, gpu_kerevalmeth=1)),
-    ((32, 30, 28), 100_000, 1e-9, np.float64, "uniform", dict(gpu_method=2)),
+    ((32, 30, 28), 100_000, 1e-3, np.float64, "uniform", dict(gpu_method=2)),            # ns = 4: the reference's 16x16x2 tile fits its 48 KB
+    ((32, 30, 28), 100_000, 1e-9, np.float64, "uniform", dict(gpu_method=2, gpu_binsizex=4, gpu_binsizey=4, gpu_binsizez=2)),   # ns = 10 needs small bins there
     ((32, 30, 28), 100_000, 1e-6, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),
     ((40, 30, 20), 100_000, 1e-3, np.float32, "onebin", dict(gpu_method=2)),     # reference spread3d_test's worst case
 ]
@@ -103,7 +104,10 @@ def test_interp_only_vs_reference(case):
     M = pts[0].size
     fw = gpuarray.to_gpu(make_modes_data(nf, dtype, seed=9)[0])      # a random fine grid [nf3][nf2][nf1]
 
-    ref = reflib.RefPlan(2, modes, tol, dtype, **opts)
+    # the reference's 1-D interpolation exists for method 1 only (src/1d/interp1d_wrapper.cu: "incorrect method,
+    # should be 1"); the arithmetic is the same, so a 1-D method-2 request of ours is checked against its method 1
+    ref_opts = dict(opts, gpu_method=1) if len(modes) == 1 else opts
+    ref = reflib.RefPlan(2, modes, tol, dtype, **ref_opts)
     ref.set_pts(dev)
     c_ref = gpuarray.zeros((M,), cd)
     ref.interp(c_ref, fw)

@@ -36,7 +36,7 @@ CASES = [
     (2, (64, 48), 20000, 1e-6, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),
     (1, (64, 48), 20000, 1e-9, np.float64, "cluster", dict(gpu_method=2, gpu_kerevalmeth=1)),
     (2, (64, 48), 20000, 1e-12, np.float64, "uniform", dict(gpu_method=2, gpu_kerevalmeth=1)),
-    (1, (24, 20, 16), 20000, 1e-6, np.float64, "uniform", dict(gpu_method=2, gpu_kerevalmeth=1)),
+    (1, (24, 20, 16), 20000, 1e-6, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),   # (method 2: the reference's tile exceeds its 48 KB at w = 7)
     (2, (24, 20, 16), 20000, 1e-9, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),
     (1, (24, 20, 16), 20000, 1e-2, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),     # w = 3
     (2, (500,), 20000, 1e-1, np.float64, "uniform", dict(gpu_method=1, gpu_kerevalmeth=1)),           # w = 2
