@@ -76,28 +76,47 @@ __device__ __forceinline__ PtRec<double> load_rec(const PtRec<double> *p)
 // ---- exp(beta*sqrt(1 - c x^2)) for |x| < ns/2, un-normalised as in the reference
 // (src/cuspreadinterp.h:6-16, which evaluates sqrt and exp in double even in the fp32 build).
 // Both versions are straight-line code without the special-case branches of libdevice:
-//   sqrt(t), t in [0,1]: MUFU rsqrt seed + Newton steps;  exp(y), y in [0, 40]: y = n ln2 + r,
+//   sqrt(t), t in (0,1]: MUFU rsqrt seed + Newton steps;  exp(y), y in [0, 40]: y = n ln2 + r,
 //   2^n applied to the exponent field.
-// fp32: argument reduction in two-term precision + ex2.approx: relative error ~1e-7 per weight
-//       (the reference's own double->float rounding is 6e-8).   fp64: degree-13 polynomial, ~1 ulp.
-__device__ __forceinline__ float es_eval(float ax, float es_c, float es_beta, float half)
+// fp32 (14 instructions, 2 MUFU): s = sqrt(t) by one Newton step; the exponent in base 2 is formed as
+//   s * (beta log2 e) with the constant split in two floats (no rounding of beta*s), n by the
+//   1.5*2^23 rounding trick, 2^f by ex2.approx, 2^n added into the exponent field with one integer op.
+//   Relative error ~1e-7 per weight plus beta * (the 6e-8 rounding of t) / (2 s).   fp64: degree-13
+//   polynomial, ~1 ulp.
+// The argument may have either sign.  |x| >= ns/2 (where the reference returns 0) is the CALLER's case:
+// inside a stencil it can only be the first point, kernel_vector handles it.
+struct EsConst32 { float c, bl_hi, bl_lo; };
+__device__ __forceinline__ EsConst32 es_const(float es_c, float es_beta)
 {
-    const float t = fmaf(-es_c * ax, ax, 1.0f);
+    const float L = 1.4426950216293335f, Llo = 1.9259629911266175e-08f;     // log2(e) = L + Llo
+    EsConst32 k;
+    k.c = es_c;
+    k.bl_hi = es_beta * L;
+    k.bl_lo = fmaf(es_beta, Llo, fmaf(es_beta, L, -k.bl_hi));
+    return k;
+}
+__device__ __forceinline__ float es_eval32(float a, const EsConst32 &k)
+{
+    float t = fmaf(-k.c * a, a, 1.0f);
+    t = fmaxf(t, 1e-30f);                    // support edge: keep rsqrt finite (the weight there is exp(0) either way)
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
     float s = t * r;
     const float e = fmaf(-s, s, t);
     s = fmaf(e * 0.5f, r, s);
-    s = t > 0.0f ? s : 0.0f;                 // support edge: rsqrt(0) = inf
-    const float y = es_beta * s;
-    const float L = 1.4426950216293335f, Llo = 1.9259629911266175e-08f;     // log2(e) = L + Llo
-    const float n = rintf(y * L);
-    float f = fmaf(y, L, -n);
-    f = fmaf(y, Llo, f);
-    float p, q;
+    const float magic = 12582912.0f;         // 1.5 * 2^23: z's low mantissa bits hold n = rint(s * beta log2 e)
+    const float z = fmaf(s, k.bl_hi, magic);
+    const float n = z - magic;
+    float f = fmaf(s, k.bl_hi, -n);
+    f = fmaf(s, k.bl_lo, f);
+    float p;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(n));                   // exact power of two
-    return ax < half ? p * q : 0.0f;
+    return __int_as_float(__float_as_int(p) + (__float_as_int(z) << 23));      // p * 2^n (the magic's own bits shift out)
+}
+__device__ __forceinline__ float es_eval(float ax, float es_c, float es_beta, float half)
+{
+    const float v = es_eval32(ax, es_const(es_c, es_beta));
+    return ax < half ? v : 0.0f;
 }
 __device__ __forceinline__ double es_eval(double ax, double es_c, double es_beta, double half)
 {
@@ -146,7 +165,19 @@ template <typename T, int NS, bool UNROLL>
 __device__ __forceinline__ void kernel_vector(T *dst, T x1, T es_c, T es_beta, bool horner, const T *hc, int ncoef)
 {
     if (!horner) {
-        if (UNROLL) {
+        if constexpr (sizeof(T) == 4) {
+            // x1 = xstart - x_r lies in [-ns/2, -ns/2 + 1): |x1 + i| < ns/2 for every i >= 1, and for i = 0
+            // unless x1 == -ns/2 exactly (then the reference's abs(x) < ns/2 test gives 0)
+            const EsConst32 k = es_const(es_c, es_beta);
+            if (UNROLL) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) dst[i] = es_eval32(x1 + (T)i, k);
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < NS; ++i) dst[i] = es_eval32(x1 + (T)i, k);
+            }
+            if (!(x1 > (T)(-0.5 * NS))) dst[0] = 0;
+        } else if (UNROLL) {
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
                 T a = x1 + (T)i;

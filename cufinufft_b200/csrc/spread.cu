@@ -2,6 +2,7 @@
 // choice of the shared-memory tile geometry for the SM spread engine.
 #include <algorithm>
 #include "spreadinterp.cuh"
+#include "spread_sm2.cuh"
 
 namespace cfb {
 
@@ -32,8 +33,27 @@ int stage_interp(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *
 // served per half-warp over 16 8-byte bank pairs, 16-byte cells per quarter-warp over 8.
 static int layout_cost(int dim, int ns, int sy, int sz, int cell_bytes)
 {
-    const int R = 32 / ns, rows = dim == 1 ? 1 : (dim == 2 ? ns : ns * ns), iters = (rows + R - 1) / R;
     const int group = cell_bytes == 8 ? 16 : 8, nbank = group;
+    if (cell_bytes == 8 && dim >= 2 && sm2_applies(dim, ns) && !sm2_map(dim, ns).single) {
+        // second-generation fp32 engine (spread_sm2.cuh): lane = (row slot, column pair); a run flush reads
+        // and writes, per pass, the cell at column xp and the cell at column xp + XP of the lane's row
+        const Sm2Map m = sm2_map(dim, ns);
+        int cost = 0;
+        for (int it = 0; it < m.npass; ++it)
+            for (int half = 0; half < 2; ++half)
+                for (int g0 = 0; g0 < 32; g0 += group) {
+                    int mult[16] = {0}, worst = 0;
+                    for (int lane = g0; lane < g0 + group; ++lane) {
+                        const int r = lane / m.xp, xp = lane - r * m.xp, row = it * m.r + r, col = xp + half * m.xp;
+                        if (lane >= m.r * m.xp || row >= m.rows || col >= ns) continue;
+                        const int iz = dim == 3 ? row / ns : 0, iy = dim == 3 ? row - iz * ns : row;
+                        worst = std::max(worst, ++mult[(iz * sz + iy * sy + col) % nbank]);
+                    }
+                    cost += worst;
+                }
+        return cost;
+    }
+    const int R = 32 / ns, rows = dim == 1 ? 1 : (dim == 2 ? ns : ns * ns), iters = (rows + R - 1) / R;
     int cost = 0;
     for (int it = 0; it < iters; ++it) {
         for (int g0 = 0; g0 < 32; g0 += group) {

@@ -1,0 +1,315 @@
+// spread_sm2.cuh -- the single-precision shared-memory spreading engine (gpu_method 2), second
+// generation.  Replaces Spread_{2,3}d_Subprob[_Horner] (src/2d/spreadinterp2d.cu:153-312,
+// src/3d/spreadinterp3d.cu:180-389) for fp32 in 2-D and in 3-D up to ns = 7 (BASELINE configs 1, 3, 4);
+// spread_sm_kernel (spreadinterp.cuh) keeps serving fp64, 1-D and the very wide 3-D stencils.
+//
+// Same decomposition as spread_sm_kernel -- a warp owns a private padded tile of one (internal) bin,
+// phase A is thread-per-point, phase B lane-per-cell with lane = (row slot r, column ix), runs of
+// points with one stencil origin are accumulated in registers and added to the tile once -- but the
+// instruction stream is rebuilt around what ncu showed for the first generation on config 3
+// (profiles/r01y: 77 warp instructions per point, 8 of them FFMA2):
+//   * lane = (row slot, column PAIR): a lane owns columns xp and xp + ceil(ns/2) of its rows.  Phase A
+//     writes the operands in the form phase B needs them: per pair (c_re kx_a, c_re kx_b, c_im kx_a,
+//     c_im kx_b) and per row slot the row weights of all passes (ky*kz).  Phase B per point and lane is
+//     ONE 16-byte load for the pair, one for (up to four) passes' weights, and per pass two FFMA2 whose
+//     scalar operand is the row weight (FFMA2 broadcasts a 32-bit source): no multiplies, no packing.
+//     The second generation's first cut (lane per cell, 8 passes) spent 12 of its 19 shared-memory
+//     wavefronts per point on these loads and ran at 68 % of the shared-memory pipe (profiles/r02b);
+//     pairs of columns need 8.
+//   * one loop over the points of a batch; a new run is a warp-uniform branch around the flush
+//     (no per-run loop set-up, no separate point-by-point path); the next point's operands are
+//     loaded before the current point's FFMA2s (explicit two-stage pipeline: the kernel runs with
+//     ~2.5 warps per scheduler, latency has to be hidden inside the warp).
+//   * the run flush uses per-lane row offsets kept in registers: LDS.64 / 2 FADD / STS.64 per pass.
+//   * tile -> fine grid row by row over the touched box (row arithmetic is warp-uniform, lanes over x,
+//     two rows in flight), zero cells skipped, vector RED.
+//   * stencils that fit one pass of lane-per-cell (2-D ns <= 5: configs 1 and 4) pair (re, im) instead:
+//     one FFMA2 per point and lane.
+#pragma once
+#include "spreadinterp.cuh"
+
+namespace cfb {
+
+template <int DIM, int NS> struct Geo2 {
+    static_assert(DIM == 2 || DIM == 3, "2-D and 3-D only");
+    static constexpr int ROWS = DIM == 2 ? NS : NS * NS;               // stencil rows (y, or (y, z) flattened)
+    // SINGLE: the whole stencil in one pass with lane = (row, column); the FFMA2 pairs (re, im)
+    static constexpr bool SINGLE = ROWS <= 32 / NS;
+    // otherwise lane = (row slot, column pair): a lane owns columns xp and xp + XP of its rows; the FFMA2
+    // pairs those two columns and takes the row weight as its scalar (broadcast) operand
+    static constexpr int XP = (NS + 1) / 2;
+    static constexpr int R = SINGLE ? 32 / NS : 32 / XP;               // stencil rows per pass
+    static constexpr int LANES = SINGLE ? R * NS : R * XP;
+    static constexpr int NPASS = SINGLE ? 1 : (ROWS + R - 1) / R;
+    static constexpr int WS = SINGLE ? 2 : (NPASS <= 2 ? NPASS : roundup(NPASS, 4));   // floats per row slot
+    static constexpr int CKSEG = SINGLE ? roundup(2 * NS, 4) : 4 * XP;
+    static constexpr int WSEG = roundup(R * WS, 4);
+    static constexpr int SLOT = (((CKSEG + WSEG) / 4) | 1) * 4;        // odd in 16-byte units: phase A's vector stores are conflict free
+    static constexpr int NSLOT = 33;                                   // one spare slot: the pipeline reads one point ahead
+    static constexpr size_t SCRATCH = (size_t)NSLOT * SLOT * sizeof(float) + 32 * sizeof(int);
+    static constexpr int MAXW = NPASS > 8 ? 8 : 16;                    // warps per block (register budget)
+};
+
+constexpr bool sm2_applies(int dim, int ns) { return dim == 2 || (dim == 3 && ns <= 7); }
+
+// host mirror of the lane mapping, for the tile-layout search (spread.cu: layout_cost)
+struct Sm2Map { bool single; int xp, r, rows, npass; };
+inline Sm2Map sm2_map(int dim, int ns)
+{
+    Sm2Map m;
+    m.rows = dim == 2 ? ns : ns * ns;
+    m.single = m.rows <= 32 / ns;
+    m.xp = (ns + 1) / 2;
+    m.r = m.single ? 32 / ns : 32 / m.xp;
+    m.npass = m.single ? 1 : (m.rows + m.r - 1) / m.r;
+    return m;
+}
+
+// packed FP32 FMA (FFMA2) through the compiler's own builtin: the accumulators stay ordinary float2
+// values for the register allocator, and a (w, w) operand becomes the scalar-broadcast form of FFMA2
+__device__ __forceinline__ void fma2(float2 &d, float2 a, float2 b) { d = __ffma2_rn(a, b, d); }
+
+template <int DIM, int NS, bool HORNER>
+__global__ void __launch_bounds__(32 * Geo2<DIM, NS>::MAXW)
+spread_sm2_kernel(const SIArgs<float> a_in)
+{
+    using G = Geo2<DIM, NS>;
+    using C = float2;
+    SIArgs<float> a = a_in;
+    a.horner = HORNER ? 1 : 0;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *s_hc = reinterpret_cast<float *>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = (size_t)a.tile_cells * sizeof(C) + G::SCRATCH;
+    unsigned char *wbase = smem + 18 * 16 * sizeof(float) + warp * per_warp;
+    C *tile = reinterpret_cast<C *>(wbase);
+    float *slots = reinterpret_cast<float *>(wbase + (size_t)a.tile_cells * sizeof(C));
+    int *s_off = reinterpret_cast<int *>(slots + G::NSLOT * G::SLOT);
+    stage_horner<float, NS>(a, s_hc);
+
+    constexpr int NCOL = G::SINGLE ? NS : G::XP;                       // lanes per row
+    const bool active = lane < G::LANES;
+    const int r = active ? lane / NCOL : 0, ix = active ? lane - r * NCOL : 0;
+    const bool last_ok = active && (G::NPASS - 1) * G::R + r < G::ROWS;     // the last pass may run past the stencil
+    const bool b_ok = G::SINGLE || ix + G::XP < NS;                    // odd widths: the last pair has one column only
+    int tb[G::NPASS];                                                  // tile offset of this lane's (first) cell per pass
+#pragma unroll
+    for (int it = 0; it < G::NPASS; ++it) {
+        int row = it * G::R + r;
+        if (row >= G::ROWS) row = 0;
+        if (DIM == 2) tb[it] = row * a.sy + ix;
+        else { const int iz = row / NS, iy = row - iz * NS; tb[it] = iz * a.sz + iy * a.sy + ix; }
+    }
+    // this lane's operands inside a point slot
+    const float *my_ck = slots + ix * (G::SINGLE ? 2 : 4);
+    const float *my_w = slots + G::CKSEG + r * G::WS;
+
+    const int nsub = *a.nsub;
+    const long long total = (long long)nsub * a.nt;
+    for (int i = lane; i < a.tile_cells; i += 32) tile[i] = C{0.0f, 0.0f};   // clean at every item start: here once, then by every flush
+
+    for (;;) {
+        long long w = 0;
+        if (lane == 0) w = atomicAdd(a.counter, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total) break;
+        const int t = (int)(w / nsub), s = (int)(w - (long long)t * nsub);
+        int pstart, n, ox, oy, oz;
+        decode_subproblem<float, DIM>(a, s, pstart, n, ox, oy, oz);
+        const C *cin = a.c + (size_t)t * a.M;
+        C *fwt = a.fw + (size_t)t * a.fwstride;
+        const PtRec<float> *recs = a.recs + pstart;
+
+        // SINGLE: are[0] = (re, im) of the lane's cell.  Else per pass: are = re of (column xp, column xp + XP), aim = im
+        float2 are[G::NPASS], aim[G::NPASS];
+#pragma unroll
+        for (int j = 0; j < G::NPASS; ++j) { are[j] = make_float2(0.0f, 0.0f); aim[j] = make_float2(0.0f, 0.0f); }
+        int cur = -1;                                      // tile offset of the open run
+        int ylo = 1 << 30, yhi = -1, zlo = 1 << 30, zhi = -1;
+
+        auto flush_run = [&]() {
+            __syncwarp();                                  // earlier tile updates of other lanes come first
+            C *cell0 = tile + cur;
+            if constexpr (G::SINGLE) {
+                if (last_ok) {
+                    C v = cell0[tb[0]];
+                    v.x += are[0].x; v.y += are[0].y;
+                    cell0[tb[0]] = v;
+                }
+                are[0] = make_float2(0.0f, 0.0f);
+            } else {
+                C va[G::NPASS], vb[G::NPASS];
+#pragma unroll
+                for (int it = 0; it < G::NPASS; ++it)
+                    if (it < G::NPASS - 1 ? active : last_ok) {
+                        va[it] = cell0[tb[it]];
+                        if (b_ok) vb[it] = cell0[tb[it] + G::XP];
+                    }
+#pragma unroll
+                for (int it = 0; it < G::NPASS; ++it) {
+                    va[it].x += are[it].x; va[it].y += aim[it].x;
+                    vb[it].x += are[it].y; vb[it].y += aim[it].y;
+                }
+#pragma unroll
+                for (int it = 0; it < G::NPASS; ++it)
+                    if (it < G::NPASS - 1 ? active : last_ok) {
+                        cell0[tb[it]] = va[it];
+                        if (b_ok) cell0[tb[it] + G::XP] = vb[it];
+                    }
+#pragma unroll
+                for (int j = 0; j < G::NPASS; ++j) { are[j] = make_float2(0.0f, 0.0f); aim[j] = make_float2(0.0f, 0.0f); }
+            }
+        };
+
+        // software pipeline over the batches: records two batches ahead, strengths one batch ahead
+        PtRec<float> rec_cur = lane < n ? load_rec(recs + lane) : null_rec<float>();
+        PtRec<float> rec_nxt = 32 + lane < n ? load_rec(recs + 32 + lane) : null_rec<float>();
+        C c_cur = lane < n ? __ldg(cin + rec_index(rec_cur)) : C{0, 0};
+
+        for (int base = 0; base < n; base += 32) {
+            const int cnt = min(32, n - base);
+            const C c_nxt = base + 32 + lane < n ? __ldg(cin + rec_index(rec_nxt)) : C{0, 0};
+            const PtRec<float> rec_nn = base + 64 + lane < n ? load_rec(recs + base + 64 + lane) : null_rec<float>();
+            __syncwarp();                                  // phase B of the previous batch is done with the slots
+            int myoff = -2;
+            if (lane < cnt) {
+                // ---- phase A: kernel values and the operands of phase B, one point per thread
+                float kx[NS], ky[NS], kz[DIM == 3 ? NS : 1];
+                const int xs = stencil_start(rec_cur.x, NS), ys = stencil_start(rec_cur.y, NS);
+                kernel_vector<float, NS, true>(kx, (float)xs - rec_cur.x, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+                kernel_vector<float, NS, true>(ky, (float)ys - rec_cur.y, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+                int zs = 0;
+                if (DIM == 3) {
+                    zs = stencil_start(rec_cur.z, NS);
+                    kernel_vector<float, NS, true>(kz, (float)zs - rec_cur.z, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
+                    zs -= a.zshift;                        // weights from the global coordinate, grid index slab-local
+                }
+                float4 *slot = reinterpret_cast<float4 *>(slots + lane * G::SLOT);
+                auto wrow = [&](int row) -> float {
+                    if (row >= G::ROWS) return 0.0f;
+                    if (DIM == 2) return ky[row];
+                    return ky[row % NS] * kz[row / NS];
+                };
+                auto ckv = [&](int i, int comp) -> float { return i < NS ? (comp ? c_cur.y : c_cur.x) * kx[i] : 0.0f; };
+                if constexpr (G::SINGLE) {
+#pragma unroll
+                    for (int i = 0; i < G::CKSEG / 4; ++i)
+                        slot[i] = make_float4(ckv(2 * i, 0), ckv(2 * i, 1), ckv(2 * i + 1, 0), ckv(2 * i + 1, 1));
+                    auto wv = [&](int rr) -> float { return rr < G::R ? wrow(rr) : 0.0f; };
+#pragma unroll
+                    for (int i = 0; i < G::WSEG / 4; ++i)
+                        slot[G::CKSEG / 4 + i] = make_float4(wv(2 * i), wv(2 * i), wv(2 * i + 1), wv(2 * i + 1));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < G::XP; ++i)
+                        slot[i] = make_float4(ckv(i, 0), ckv(i + G::XP, 0), ckv(i, 1), ckv(i + G::XP, 1));
+                    // row slot rr, pass it -> flat float index rr*WS + it inside the W segment
+                    auto wv = [&](int f) -> float {
+                        const int rr = f / G::WS, it = f - rr * G::WS;
+                        return (rr < G::R && it < G::NPASS) ? wrow(it * G::R + rr) : 0.0f;
+                    };
+#pragma unroll
+                    for (int i = 0; i < G::WSEG / 4; ++i)
+                        slot[G::CKSEG / 4 + i] = make_float4(wv(4 * i), wv(4 * i + 1), wv(4 * i + 2), wv(4 * i + 3));
+                }
+                myoff = clampi(xs - ox, 0, a.ex - NS);
+                { const int yo = clampi(ys - oy, 0, a.ey - NS); myoff += yo * a.sy; ylo = min(ylo, yo); yhi = max(yhi, yo); }
+                if (DIM == 3) { const int zo = clampi(zs - oz, 0, a.ez - NS); myoff += zo * a.sz; zlo = min(zlo, zo); zhi = max(zhi, zo); }
+                s_off[lane] = myoff;
+            }
+            __syncwarp();
+            int prev = __shfl_up_sync(0xffffffffu, myoff, 1);
+            if (lane == 0) prev = cur;
+            const unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && myoff != prev);
+
+            // ---- phase B: one loop over the points, operands one point ahead
+            if constexpr (G::SINGLE) {
+                float2 A = *reinterpret_cast<const float2 *>(my_ck);
+                float2 W = *reinterpret_cast<const float2 *>(my_w);
+#pragma unroll 4
+                for (int q = 0; q < cnt; ++q) {
+                    const float2 An = *reinterpret_cast<const float2 *>(my_ck + (q + 1) * G::SLOT);
+                    const float2 Wn = *reinterpret_cast<const float2 *>(my_w + (q + 1) * G::SLOT);
+                    if ((starts >> q) & 1u) {
+                        if (cur >= 0) flush_run();
+                        cur = s_off[q];
+                    }
+                    fma2(are[0], A, W);
+                    A = An; W = Wn;
+                }
+            } else {
+                struct Ops { float4 a; float w[G::WS]; };
+                auto load_ops = [&](int q) -> Ops {
+                    Ops o;
+                    o.a = *reinterpret_cast<const float4 *>(my_ck + q * G::SLOT);
+                    const float *pw = my_w + q * G::SLOT;
+                    if constexpr (G::WS == 1) o.w[0] = pw[0];
+                    else if constexpr (G::WS == 2) { const float2 v = *reinterpret_cast<const float2 *>(pw); o.w[0] = v.x; o.w[1] = v.y; }
+                    else {
+#pragma unroll
+                        for (int j = 0; j < G::WS / 4; ++j) {
+                            const float4 v = reinterpret_cast<const float4 *>(pw)[j];
+                            o.w[4 * j] = v.x; o.w[4 * j + 1] = v.y; o.w[4 * j + 2] = v.z; o.w[4 * j + 3] = v.w;
+                        }
+                    }
+                    return o;
+                };
+                Ops o = load_ops(0);
+#pragma unroll 2
+                for (int q = 0; q < cnt; ++q) {
+                    const Ops on = load_ops(q + 1);
+                    if ((starts >> q) & 1u) {
+                        if (cur >= 0) flush_run();
+                        cur = s_off[q];
+                    }
+                    const float2 pre = make_float2(o.a.x, o.a.y), pim = make_float2(o.a.z, o.a.w);
+#pragma unroll
+                    for (int it = 0; it < G::NPASS; ++it) {
+                        const float2 ww = make_float2(o.w[it], o.w[it]);
+                        fma2(are[it], ww, pre);
+                        fma2(aim[it], ww, pim);
+                    }
+                    o = on;
+                }
+            }
+            rec_cur = rec_nxt; rec_nxt = rec_nn; c_cur = c_nxt;
+        }
+        if (cur >= 0) flush_run();
+        __syncwarp();
+
+        // ---- tile -> fine grid, row by row over the touched box [nz][ny] x ex: lanes over x, two rows in
+        // flight; zero cells are skipped, the tile is cleared on the way.  Single periodic wrap (the
+        // reference's guard ix < nf + pad, src/2d/spreadinterp2d.cu:222-224, is implied: cells beyond it are
+        // never touched and stay zero).
+        {
+            ylo = __reduce_min_sync(0xffffffffu, ylo); yhi = __reduce_max_sync(0xffffffffu, yhi);
+            if (DIM == 3) { zlo = __reduce_min_sync(0xffffffffu, zlo); zhi = __reduce_max_sync(0xffffffffu, zhi); }
+            const int ex = a.ex;
+            const int ny = yhi < 0 ? 0 : yhi - ylo + NS;
+            const int nz = DIM == 3 ? zhi - zlo + NS : 1;
+            const int z0 = DIM == 3 ? zlo : 0;
+            const size_t plane = (size_t)a.nf1 * a.nf2;
+            for (int lz = 0; lz < nz; ++lz) {
+                C *tz = tile + (z0 + lz) * a.sz + ylo * a.sy;
+                C *gz = fwt + (DIM == 3 ? (size_t)wrap_index(oz + z0 + lz, a.nf3) * plane : 0);
+                for (int ly = 0; ly < ny; ly += 2) {
+                    C *t0 = tz + ly * a.sy, *t1 = t0 + a.sy;
+                    const bool two = ly + 1 < ny;
+                    C *g0 = gz + (size_t)wrap_index(oy + ylo + ly, a.nf2) * a.nf1;
+                    C *g1 = gz + (size_t)wrap_index(oy + ylo + ly + 1, a.nf2) * a.nf1;
+                    for (int lx = lane; lx < ex; lx += 32) {
+                        const C v0 = t0[lx];
+                        C v1 = C{0.0f, 0.0f};
+                        if (two) v1 = t1[lx];
+                        const int gx = wrap_index(ox + lx, a.nf1);
+                        if (v0.x != 0.0f || v0.y != 0.0f) { red_add(g0 + gx, v0.x, v0.y); t0[lx] = C{0.0f, 0.0f}; }
+                        if (v1.x != 0.0f || v1.y != 0.0f) { red_add(g1 + gx, v1.x, v1.y); t1[lx] = C{0.0f, 0.0f}; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace cfb

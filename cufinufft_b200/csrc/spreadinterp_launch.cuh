@@ -7,8 +7,10 @@
 // src/2d/interp2d_wrapper.cu:88-274 and the 1-D / 3-D twins): here ONE launch covers
 // all transforms of the batch.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include "spreadinterp.cuh"
+#include "spread_sm2.cuh"
 
 namespace cfb {
 
@@ -50,6 +52,26 @@ static int do_spread_h(Plan<T> &p, SIArgs<T> &a)
 {
     using C = typename Plan<T>::C;
     const size_t head = 18 * 16 * sizeof(T);
+    if constexpr (sizeof(T) == 4 && DIM >= 2 && sm2_applies(DIM, NS)) {
+        // single precision, 2-D / 3-D up to ns = 7: the second-generation SM engine (spread_sm2.cuh);
+        // CFB_SM_GEN=1 keeps the first one (A/B measurements)
+        static const bool gen1 = [] { const char *e = getenv("CFB_SM_GEN"); return e && e[0] == '1'; }();
+        if (p.method == 2 && p.sm_warps > 0 && !gen1) {
+            const size_t per_warp = (size_t)p.tile_cells * sizeof(C) + Geo2<DIM, NS>::SCRATCH;
+            int warps = std::min(p.sm_warps, Geo2<DIM, NS>::MAXW);
+            while (warps > 1 && head + (size_t)warps * per_warp + 1024 > (size_t)p.max_smem_optin) --warps;
+            const size_t smem = head + (size_t)warps * per_warp;
+            CFB_CUDA_OK(cudaFuncSetAttribute(spread_sm2_kernel<DIM, NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int blocks_per_sm = (int)((size_t)p.max_smem_optin / (smem + 1024));
+            if (blocks_per_sm < 1) blocks_per_sm = 1;
+            if (blocks_per_sm * warps > 32) blocks_per_sm = 32 / warps > 0 ? 32 / warps : 1;
+            CFB_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(int), p.stream));
+            spread_sm2_kernel<DIM, NS, HORNER><<<p.num_sms * blocks_per_sm, 32 * warps, smem, p.stream>>>(a);
+            p.launches_exec++;
+            CFB_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+    }
     if (p.method == 2 && p.sm_warps > 0) {
         size_t per_warp = (size_t)p.tile_cells * sizeof(C) + warp_scratch_bytes<T, DIM, NS, false>();
         size_t smem = head + (size_t)p.sm_warps * per_warp;
@@ -162,7 +184,11 @@ struct NsDispatch {
         return NsDispatch<T, DIM, NS - 1>::interp(p, a);
     }
     static size_t scratch(int ns) {
-        if (ns == NS) return warp_scratch_bytes<T, DIM, NS, false>();
+        if (ns == NS) {
+            if constexpr (sizeof(T) == 4 && DIM >= 2 && sm2_applies(DIM, NS))
+                return std::max(warp_scratch_bytes<T, DIM, NS, false>(), (size_t)Geo2<DIM == 1 ? 2 : DIM, NS>::SCRATCH);
+            return warp_scratch_bytes<T, DIM, NS, false>();
+        }
         return NsDispatch<T, DIM, NS - 1>::scratch(ns);
     }
 };

@@ -83,7 +83,7 @@ def test_dense_inputs_get_more_resident_warps():
     w = workplan(1, (256, 256, 256), 1e-5, np.float32, 100_000_000)
     per_warp = w["tile_cells"] * 8
     assert w["nibins"] > w["nbins"] and per_warp <= 16 * 1024
-    assert w["ibsx"] == 16                                                 # x keeps the conflict-free stride of 22 cells
+    assert w["ibsx"] * w["ibsy"] * w["ibsz"] == 128                         # two halvings of the 16x16x2 bin
     assert w["imaxsub"] == 100_000_000 // (16 * 148 * 16)                 # larger work items (one tile flush each), >= 16 per resident warp
     # config 1: the 36x36 tile + the single-pass scratch already fit the 14 KB per-warp target; never
     # fewer than 64 points per (sub-)bin
