@@ -120,10 +120,12 @@ host_workplan = _bind("cufinufft_b200_host_workplan", [c_int, c_int, c_int_p, c_
 phihat_quadrature = _bind("cufinufft_b200_phihat_quadrature", [c_int, c_int, c_double, c_double, c_double, c_int,
                                                                c_void_p, c_void_p])
 
+microbench = _bind("cufinufft_b200_microbench", [c_int, c_int, POINTER(c_double)])
+
 C_ABI_SYMBOLS = [base % s for s in ("", "f") for base in (
     "cufinufft%s_default_opts", "cufinufft%s_makeplan", "cufinufft%s_setpts", "cufinufft%s_execute",
     "cufinufft%s_destroy")]
-EXTENSION_SYMBOLS = ["cufinufft_b200_version", "cufinufft_b200_host_params", "cufinufft_b200_host_workplan", "cufinufft_b200_phihat_quadrature"] + [base % s for s in ("", "f") for base in (
+EXTENSION_SYMBOLS = ["cufinufft_b200_version", "cufinufft_b200_host_params", "cufinufft_b200_host_workplan", "cufinufft_b200_phihat_quadrature", "cufinufft_b200_microbench"] + [base % s for s in ("", "f") for base in (
     "cufinufft%s_set_stream", "cufinufft%s_setpts_host", "cufinufft%s_execute_host", "cufinufft%s_spread",
     "cufinufft%s_interp", "cufinufft%s_get_ints", "cufinufft%s_get_reals", "cufinufft%s_set_timing",
     "cufinufft%s_get_timing", "cufinufft%s_get_launch_counts", "cufinufft%s_set_interp_engine", "cufinufft%s_set_sort_levels",

@@ -1,6 +1,7 @@
 // spread.cu -- dimension dispatch for the spread / interp stages and the plan-time
 // choice of the shared-memory tile geometry for the SM spread engine.
 #include <algorithm>
+#include <cstdlib>
 #include "spreadinterp.cuh"
 #include "spread_sm2.cuh"
 
@@ -138,10 +139,12 @@ void choose_internal_bins(Plan<T> &p, long long M)
     // items of up to 4096 points -- as long as >= 16 items per resident warp remain for balance.
     {
         const long long per_item = M / (16LL * p.num_sms * 16);
-        const long long lo = p.opts.gpu_maxsubprobsize, hi = 4096;
+        static const long long hi_env = [] { const char *e = getenv("CFB_SM_MAXITEM"); return e ? atoll(e) : 0LL; }();   // experiments
+        const long long lo = p.opts.gpu_maxsubprobsize, hi = hi_env > 0 ? hi_env : 4096;
         p.imaxsub = (int)(per_item < lo ? lo : (per_item > hi ? (hi > lo ? hi : lo) : per_item));
     }
-    const size_t target = 14 * 1024;
+    static const size_t target_env = [] { const char *e = getenv("CFB_SM_TARGET_KB"); return e ? (size_t)atoll(e) * 1024 : (size_t)0; }();   // experiments
+    const size_t target = target_env ? target_env : 14 * 1024;
     for (;;) {
         size_t per_warp;
         switch (p.dim) {

@@ -26,6 +26,7 @@
 //   * stencils that fit one pass of lane-per-cell (2-D ns <= 5: configs 1 and 4) pair (re, im) instead:
 //     one FFMA2 per point and lane.
 #pragma once
+#include <type_traits>
 #include "spreadinterp.cuh"
 
 namespace cfb {
@@ -216,6 +217,12 @@ spread_sm2_kernel(const SIArgs<float> a_in)
                 { const int yo = clampi(ys - oy, 0, a.ey - NS); myoff += yo * a.sy; ylo = min(ylo, yo); yhi = max(yhi, yo); }
                 if (DIM == 3) { const int zo = clampi(zs - oz, 0, a.ez - NS); myoff += zo * a.sz; zlo = min(zlo, zo); zhi = max(zhi, zo); }
                 s_off[lane] = myoff;
+            } else if (cnt < 32) {
+                // short (last) batch: phase B runs whole groups of four points, the surplus ones add zeros
+                // (both operand segments: 0 x a stale NaN would still be NaN)
+                float4 *slot = reinterpret_cast<float4 *>(slots + lane * G::SLOT);
+#pragma unroll
+                for (int i = 0; i < (G::CKSEG + G::WSEG) / 4; ++i) slot[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
             __syncwarp();
             int prev = __shfl_up_sync(0xffffffffu, myoff, 1);
@@ -254,14 +261,7 @@ spread_sm2_kernel(const SIArgs<float> a_in)
                     }
                     return o;
                 };
-                Ops o = load_ops(0);
-#pragma unroll 2
-                for (int q = 0; q < cnt; ++q) {
-                    const Ops on = load_ops(q + 1);
-                    if ((starts >> q) & 1u) {
-                        if (cur >= 0) flush_run();
-                        cur = s_off[q];
-                    }
+                auto accumulate = [&](const Ops &o) {
                     const float2 pre = make_float2(o.a.x, o.a.y), pim = make_float2(o.a.z, o.a.w);
 #pragma unroll
                     for (int it = 0; it < G::NPASS; ++it) {
@@ -269,7 +269,31 @@ spread_sm2_kernel(const SIArgs<float> a_in)
                         fma2(are[it], ww, pre);
                         fma2(aim[it], ww, pim);
                     }
-                    o = on;
+                };
+                Ops o = load_ops(0);
+                // groups of four points: a group without a run start (about half of them on dense inputs) is
+                // straight-line code; the others test every point
+                for (int q0 = 0; q0 < cnt; q0 += 4) {
+                    const unsigned m = (starts >> q0) & 0xfu;
+                    if (m == 0u) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const Ops on = load_ops(q0 + j + 1);
+                            accumulate(o);
+                            o = on;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const Ops on = load_ops(q0 + j + 1);
+                            if ((m >> j) & 1u) {
+                                if (cur >= 0) flush_run();
+                                cur = s_off[q0 + j];
+                            }
+                            accumulate(o);
+                            o = on;
+                        }
+                    }
                 }
             }
             rec_cur = rec_nxt; rec_nxt = rec_nn; c_cur = c_nxt;
@@ -277,10 +301,11 @@ spread_sm2_kernel(const SIArgs<float> a_in)
         if (cur >= 0) flush_run();
         __syncwarp();
 
-        // ---- tile -> fine grid, row by row over the touched box [nz][ny] x ex: lanes over x, two rows in
-        // flight; zero cells are skipped, the tile is cleared on the way.  Single periodic wrap (the
-        // reference's guard ix < nf + pad, src/2d/spreadinterp2d.cu:222-224, is implied: cells beyond it are
-        // never touched and stay zero).
+        // ---- tile -> fine grid over the touched box [nz][ny] x ex: lanes over (rows of the box, x) -- several
+        // rows per warp pass when the tile is narrow --, two passes in flight; zero cells are skipped, the tile
+        // is cleared on the way.  Boxes that do not cross the periodic boundary (all but the outermost bins)
+        // take the path without index wrapping.  (The reference's guard ix < nf + pad,
+        // src/2d/spreadinterp2d.cu:222-224, is implied: cells beyond it are never touched and stay zero.)
         {
             ylo = __reduce_min_sync(0xffffffffu, ylo); yhi = __reduce_max_sync(0xffffffffu, yhi);
             if (DIM == 3) { zlo = __reduce_min_sync(0xffffffffu, zlo); zhi = __reduce_max_sync(0xffffffffu, zhi); }
@@ -288,25 +313,49 @@ spread_sm2_kernel(const SIArgs<float> a_in)
             const int ny = yhi < 0 ? 0 : yhi - ylo + NS;
             const int nz = DIM == 3 ? zhi - zlo + NS : 1;
             const int z0 = DIM == 3 ? zlo : 0;
+            const int nrows = ny * nz;
+            const int rpi = ex >= 32 ? 1 : 32 / ex;                     // box rows per warp pass
+            const int lr = ex >= 32 ? 0 : lane / ex, lx0 = lane - lr * ex;
+            const bool lane_on = lr < rpi;
+            const int gy0 = oy + ylo, gz0 = oz + z0;
+            const bool nowrap = ox >= 0 && ox + ex <= a.nf1 && gy0 >= 0 && gy0 + ny <= a.nf2 &&
+                                (DIM == 2 || (gz0 >= 0 && gz0 + nz <= a.nf3));
             const size_t plane = (size_t)a.nf1 * a.nf2;
-            for (int lz = 0; lz < nz; ++lz) {
-                C *tz = tile + (z0 + lz) * a.sz + ylo * a.sy;
-                C *gz = fwt + (DIM == 3 ? (size_t)wrap_index(oz + z0 + lz, a.nf3) * plane : 0);
-                for (int ly = 0; ly < ny; ly += 2) {
-                    C *t0 = tz + ly * a.sy, *t1 = t0 + a.sy;
-                    const bool two = ly + 1 < ny;
-                    C *g0 = gz + (size_t)wrap_index(oy + ylo + ly, a.nf2) * a.nf1;
-                    C *g1 = gz + (size_t)wrap_index(oy + ylo + ly + 1, a.nf2) * a.nf1;
-                    for (int lx = lane; lx < ex; lx += 32) {
-                        const C v0 = t0[lx];
-                        C v1 = C{0.0f, 0.0f};
-                        if (two) v1 = t1[lx];
-                        const int gx = wrap_index(ox + lx, a.nf1);
+            auto sweep = [&](auto wrap_tag) {
+                constexpr bool WRAP = decltype(wrap_tag)::value;
+                int ly = lr, lz = 0;                                   // this lane's row of the current pass
+                while (ly >= ny && ny > 0) { ly -= ny; ++lz; }
+                auto step = [&]() { ly += rpi; while (ly >= ny) { ly -= ny; ++lz; } };
+                auto cell_ptrs = [&](int row, C *&tp, C *&gp, bool &on) {
+                    on = lane_on && row < nrows;
+                    tp = tile + (z0 + lz) * a.sz + (ylo + ly) * a.sy;
+                    if (WRAP) {
+                        gp = fwt + (size_t)wrap_index(gy0 + ly, a.nf2) * a.nf1;
+                        if (DIM == 3) gp += (size_t)wrap_index(gz0 + lz, a.nf3) * plane;
+                    } else {
+                        gp = fwt + (size_t)(gy0 + ly) * a.nf1 + ox;
+                        if (DIM == 3) gp += (size_t)(gz0 + lz) * plane;
+                    }
+                };
+                for (int row0 = 0; row0 < nrows; row0 += 2 * rpi) {
+                    C *t0, *t1, *g0, *g1;
+                    bool on0, on1;
+                    cell_ptrs(row0 + lr, t0, g0, on0);
+                    step();
+                    cell_ptrs(row0 + rpi + lr, t1, g1, on1);
+                    step();
+                    for (int lx = lx0; lx < ex; lx += 32) {
+                        C v0 = C{0.0f, 0.0f}, v1 = C{0.0f, 0.0f};
+                        if (on0) v0 = t0[lx];
+                        if (on1) v1 = t1[lx];
+                        const int gx = WRAP ? wrap_index(ox + lx, a.nf1) : lx;
                         if (v0.x != 0.0f || v0.y != 0.0f) { red_add(g0 + gx, v0.x, v0.y); t0[lx] = C{0.0f, 0.0f}; }
                         if (v1.x != 0.0f || v1.y != 0.0f) { red_add(g1 + gx, v1.x, v1.y); t1[lx] = C{0.0f, 0.0f}; }
                     }
                 }
-            }
+            };
+            if (nowrap) sweep(std::false_type{});
+            else sweep(std::true_type{});
         }
         __syncwarp();
     }

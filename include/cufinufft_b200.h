@@ -60,6 +60,14 @@ int cufinufft_b200_phihat_quadrature(int nf, int ns, double beta, double es_c, d
 int cufinufft_b200_host_workplan(int type, int dim, const int *nmodes, double tol, int single_precision,
                                  const cufinufft_opts *opts, long long M, int *out_ints16);
 
+/* Measured peak of one SM resource on `device`, whole GPU (csrc/microbench.cu; SURVEY.md 8d asks for measured,
+ * not nominal, denominators of the binding-resource roofline):
+ *   what 0 shared-memory read bandwidth (conflict-free LDS.128), bytes/s     1 FFMA2 (fma.rn.f32x2), FMA/s
+ *        2 scalar FFMA, FMA/s      3 DFMA, FMA/s      4 shared-memory atomicAdd(float), conflict-free, atomics/s
+ *        5 shared-memory read bandwidth through LDS.64, bytes/s
+ * Runs a few ms of synthetic kernels on the device's default stream. */
+int cufinufft_b200_microbench(int what, int device, double *out);
+
 /* Stream on which all work of the plan is enqueued (default: the calling thread's per-thread default
  * stream, cudaStreamPerThread, as in the reference build).
  * `stream` is a cudaStream_t passed as void*. */
