@@ -62,6 +62,10 @@ CONFIGS = {
     8: dict(name="cfg3-onebin: 3D type 1 fp32 256^3 M=1e8 all points in one 16-cell corner (spread3d_test worst case) tol=1e-5 method 2",
             type=1, modes=(256, 256, 256), M=100_000_000, tol=1e-5, dtype="float32", dist="onebin", ntransf=1,
             opts=dict(gpu_method=2)),
+    # profiling stand-in for config 5's kernel: same stencil, bins and point density (477 per bin) on an eighth of the grid
+    9: dict(name="cfg5-eighth: 3D type 2 fp64 256^3 (512^3 fine grid) M=1.25e8 uniform tol=1e-9 (config 5's density, one GPU, undivided plan)",
+            type=2, modes=(256, 256, 256), M=125_000_000, tol=1e-9, dtype="float64", dist="uniform", ntransf=1,
+            opts=dict(gpu_method=1, gpu_sort=1)),
 }
 
 METRIC = "NU points/s per execute"

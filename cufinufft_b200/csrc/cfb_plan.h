@@ -61,6 +61,10 @@ struct SortGeo {
     // planes zl = z_r - zshift; nf[2] is then the local plane count.  Ordinary plans: nfz = nf[2],
     // zshift = 0, zlo = 0, zhi = nf[2].
     int nfz, zshift, zlo, zhi;
+    // bank-class order (type-2 plans served by the tile interpolation engine): the key inside a bin is the
+    // point's shared-memory bank class, (its first stencil cell's index in the bin tile) mod bankc, instead of
+    // the stencil cell; the tile has bex x bey (x bez) cells and a halo of bpad.  bankc = 0: stencil-cell order.
+    int bankc, bex, bey, bez, bpad;
 };
 
 template <typename T>
@@ -121,6 +125,7 @@ struct Plan {
     int tile_cost = 0;                   // shared-memory wavefronts per point of the chosen tile layout (bank-conflict model)
     int sm_warps = 0;                    // warps per block for the SM spread kernel (0 = SM unusable)
     int interp_engine = 0;               // 0 auto (tile when sorted and it fits), 1 gather, 2 tile
+    int bank_classes = 0;                // > 0: the points of the last setpts are in bank-class order (setpts.cu)
     // z-slab decomposition of one 3-D transform (slab.cu): this plan owns the fine-grid
     // planes [z0, z1) of a global grid with nf3g planes and holds them with `tile_pad` halo planes on
     // both sides: nf3 = z1 - z0 + 2*tile_pad local planes, local plane l = global plane zshift + l.
@@ -159,6 +164,7 @@ template <typename T> int stage_deconvolve(Plan<T> &p, typename Plan<T>::C *fk, 
 template <typename T> int stage_amplify(Plan<T> &p, const typename Plan<T>::C *fk, typename Plan<T>::C *fw, int nt);
 template <typename T> void plan_tile_geometry(Plan<T> &p);                 // spread.cu
 template <typename T> void choose_internal_bins(Plan<T> &p, long long M);  // spread.cu
+template <typename T> bool interp_tile_applies(const Plan<T> &p);          // spread.cu: the tile interpolation engine will serve this plan
 // z-slab stages (slab.cu)
 template <typename T> int slab_make_ffts(Plan<T> &p);
 template <typename T> int slab_type2(Plan<T> &p, typename Plan<T>::C *c, const typename Plan<T>::C *fk);

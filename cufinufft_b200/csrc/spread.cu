@@ -176,10 +176,29 @@ void choose_internal_bins(Plan<T> &p, long long M)
     p.ilist = p.nibins != p.nbins || p.imaxsub != p.opts.gpu_maxsubprobsize;
 }
 
+// Whether the tile interpolation engine serves this plan's points (the launcher's rule, spreadinterp_launch.cuh:
+// do_interp_tile, without the occupancy query): setpts needs to know, because it orders the points of a bin by
+// shared-memory bank class for that engine and by stencil cell for the gather engine.
+template <typename T>
+bool interp_tile_applies(const Plan<T> &p)
+{
+    using C = typename Plan<T>::C;
+    if (!p.sorted || p.interp_engine == 1 || p.M <= 0) return false;
+    const int pad = (p.ns + 1) / 2;
+    const size_t cells = (size_t)(p.ibs[0] + 2 * pad) * (p.dim > 1 ? p.ibs[1] + 2 * pad : 1) * (p.dim > 2 ? p.ibs[2] + 2 * pad : 1);
+    const size_t smem = 18 * 16 * sizeof(T) + cells * sizeof(C);
+    if (smem + 1024 > (size_t)p.max_smem_optin) return false;
+    const bool sparse = (unsigned long long)p.M * 64ull < (unsigned long long)p.nbins * cells;
+    const bool planes_fit_l2 = p.dim < 3 || (long long)p.ns * p.nf1 * p.nf2 * (long long)sizeof(C) <= p.l2_bytes / 2;
+    return !(p.interp_engine == 0 && sparse && planes_fit_l2);
+}
+
 template int stage_spread<float>(Plan<float> &, const float2 *, float2 *, int);
 template int stage_spread<double>(Plan<double> &, const double2 *, double2 *, int);
 template int stage_interp<float>(Plan<float> &, float2 *, const float2 *, int);
 template int stage_interp<double>(Plan<double> &, double2 *, const double2 *, int);
+template bool interp_tile_applies<float>(const Plan<float> &);
+template bool interp_tile_applies<double>(const Plan<double> &);
 template void plan_tile_geometry<float>(Plan<float> &);
 template void plan_tile_geometry<double>(Plan<double> &);
 template void choose_internal_bins<float>(Plan<float> &, long long);

@@ -62,6 +62,7 @@ struct SIArgs {
     int sy, sz, tile_cells;     // padded tile strides
     int horner, ncoef;
     int zshift;                 // slab plans: local plane = global plane - zshift (0 otherwise)
+    int bankc;                  // > 0: the points of a bin are ordered by shared-memory bank class (cpb == bankc classes per bin)
     int thr_num, thr_den;       // tuning override of the short-run threshold (0 = built-in; env CFB_DIRECT_THR=num/den)
     T es_c, es_beta;
     long long fwstride;
@@ -908,6 +909,7 @@ interp_tile_kernel(const SIArgs<T> a_in)
     T *s_hc = reinterpret_cast<T *>(smem);
     C *tile = reinterpret_cast<C *>(smem + 18 * 16 * sizeof(T));
     __shared__ long long s_work;
+    __shared__ int s_cs[16], s_ce[16];                    // bank-class order: this item's range of every class
     stage_horner<T, NS>(a, s_hc);
 
     const int nsub = *a.nsub;
@@ -916,6 +918,15 @@ interp_tile_kernel(const SIArgs<T> a_in)
     const int rows = ey * ez;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const size_t plane = (size_t)a.nf1 * a.nf2;
+    // Bank-class order (setpts.cu; type-2 plans): the points of a bin are grouped by the shared-memory bank
+    // class of their first stencil cell, NC = 128 / sizeof(C) classes.  Thread t takes slot (class t % NC,
+    // position t / NC): the lanes that share a shared-memory wavefront (8 for 16-byte cells, 16 for 8-byte
+    // cells) then read NC different banks in EVERY stencil load -- no bank conflicts, where sorted-by-cell
+    // neighbours collide whenever their cells are a multiple of NC apart (32 % of the wavefronts of the
+    // config-5 kernel, profiles/r02f).  Classes are not equally full: slots beyond a class's last point are
+    // handed the surplus points of fuller classes, so an item still takes ceil(n / blockDim) rounds.
+    const int NC = a.bankc;
+    const int cls = NC > 0 ? (int)(threadIdx.x % NC) : 0, cap = NC > 0 ? (int)(blockDim.x / NC) : 0;
 
     for (;;) {
         __syncthreads();                                  // everybody is done with the previous tile
@@ -928,7 +939,11 @@ interp_tile_kernel(const SIArgs<T> a_in)
         decode_subproblem<T, DIM>(a, s, pstart, n, ox, oy, oz);
         C *cout = a.c + (size_t)t * a.M;
         const C *fwt = a.fw + (size_t)t * a.fwstride;
-        const PtRec<T> *recs = a.recs + pstart;
+        if (NC > 0 && threadIdx.x < NC) {                 // the class segments of this item's bin
+            const int bin = a.s2b[s];
+            s_cs[threadIdx.x] = a.keyoff[(size_t)bin * a.cpb + threadIdx.x];
+            s_ce[threadIdx.x] = a.keyoff[(size_t)bin * a.cpb + threadIdx.x + 1];
+        }
 
         // ---- tile <- fine grid (async); rows are distributed over the warps
         for (int row = warp; row < rows; row += nwarps) {
@@ -945,15 +960,49 @@ interp_tile_kernel(const SIArgs<T> a_in)
                 if (gx >= 0 && gx < a.nf1) cp_async_cell(trow + lx, grow + gx);
             }
         }
+        if (NC > 0) __syncthreads();                      // s_cls is complete
 
         // ---- thread-per-point
+        // The bin's points fill R = ceil(n_bin / blockDim) rounds of blockDim slots; slot (class, position) of
+        // round r is position r * cap + t / NC of class t % NC.  The bin's K items (one per maxsub points, the
+        // subproblem list is shared with the other engines) split the ROUNDS among themselves, so every item
+        // sees all classes and no round is partly empty except the bin's last.
+        int rnd = 0, rnd_end = 0, ccap = 0;
+        if (NC > 0) {
+            int nbin = 0;
+            for (int c = 0; c < NC; ++c) nbin += s_ce[c] - s_cs[c];
+            const int bin = a.s2b[s];
+            const int k = s - a.substart[bin], K = a.substart[bin + 1] - a.substart[bin];
+            const int R = (nbin + (int)blockDim.x - 1) / (int)blockDim.x;
+            rnd = (int)((long long)R * k / K); rnd_end = (int)((long long)R * (k + 1) / K);
+            ccap = R * cap;
+        }
+        // sorted point index (absolute) of this thread in round `rnd`, or -1
+        auto class_point = [&](int rnd) -> int {
+            const int j = rnd * cap + (int)(threadIdx.x / NC);
+            const int mine = s_ce[cls] - s_cs[cls];
+            if (j < mine) return s_cs[cls] + j;
+            // a free slot: its rank among the free slots (ordered by class, then position) ...
+            int k = j - mine;
+            for (int c = 0; c < cls; ++c) k += max(0, ccap - (s_ce[c] - s_cs[c]));
+            // ... takes the surplus point (position >= ccap in a fuller class) of the same rank
+            for (int c = 0; c < NC; ++c) {
+                const int over = (s_ce[c] - s_cs[c]) - ccap;
+                if (over > 0) {
+                    if (k < over) return s_cs[c] + ccap + k;
+                    k -= over;
+                }
+            }
+            return -1;
+        };
         bool first = true;
-        for (int i = threadIdx.x; i < n || first; i += blockDim.x) {
-            const bool valid = i < n;
+        for (int i = threadIdx.x; (NC > 0 ? rnd < rnd_end : i < n) || first; i += blockDim.x, ++rnd) {
+            const int pidx = NC > 0 ? (rnd < rnd_end ? class_point(rnd) : -1) : (i < n ? pstart + i : -1);
+            const bool valid = pidx >= 0;
             T kx[NS], ky[DIM > 1 ? NS : 1], kz[DIM > 2 ? NS : 1];
             int off = 0, idx = 0;
             if (valid) {
-                const PtRec<T> rec = load_rec(recs + i);
+                const PtRec<T> rec = load_rec(a.recs + pidx);
                 idx = rec_index(rec);
                 const int xs = stencil_start(rec.x, NS);
                 kernel_vector<T, NS, true>(kx, (T)xs - rec.x, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);

@@ -39,6 +39,7 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     a.horner = p.opts.gpu_kerevalmeth == 1; a.ncoef = p.horner_ncoef;
     a.es_c = p.es_c; a.es_beta = p.es_beta;
     a.zshift = p.slab ? p.zshift : 0;
+    a.bankc = p.bank_classes;
     // experiments only (read once per process): CFB_DIRECT_THR="num/den" = run length below which a batch goes point by point
     static const struct Thr { int n = 0, d = 1; Thr() { if (const char *e = getenv("CFB_DIRECT_THR")) { int a_ = 0, b_ = 1;
                           if (sscanf(e, "%d/%d", &a_, &b_) >= 1 && a_ > 0 && b_ > 0) { n = a_; d = b_; } } } } thr;
@@ -103,20 +104,17 @@ static int do_interp_tile(Plan<T> &p, SIArgs<T> &a, bool &done)
 {
     using C = typename Plan<T>::C;
     done = false;
-    if (!p.sorted || p.interp_engine == 1) return 0;
-    const size_t head = 18 * 16 * sizeof(T);
-    const size_t cells = (size_t)a.ex * a.ey * a.ez;
-    const size_t smem = head + cells * sizeof(C);
-    if (smem + 1024 > (size_t)p.max_smem_optin) return 0;
     // Sparse inputs: a tile of `cells` grid values is staged for every subproblem, which only pays
     // when enough points share it.  Measured crossover (tools/ab_interp.py, profiles/r01j_ab_lowdensity):
     // about one point per 64 tile cells (3-D fp64 ns=10: 127 points per bin, 2-D fp32 ns=4: 20).
     // The gather engine lives on L2 reuse between neighbouring bins, though: in 3-D it needs the ns
     // planes a stencil spans to stay resident (config 5's 1024^2 x 10 planes = 168 MB do not: measured
     // 6.1 ns/point gather vs 3.4 tile at 60 points per bin, profiles/r01zc), else the tile engine stays.
-    const bool sparse = (unsigned long long)p.M * 64ull < (unsigned long long)p.nbins * cells;
-    const bool planes_fit_l2 = DIM < 3 || (long long)NS * p.nf1 * p.nf2 * (long long)sizeof(C) <= p.l2_bytes / 2;
-    if (p.interp_engine == 0 && sparse && planes_fit_l2) return 0;
+    // (the rule itself: interp_tile_applies, spread.cu -- setpts uses it too)
+    if (!interp_tile_applies(p)) return 0;
+    const size_t head = 18 * 16 * sizeof(T);
+    const size_t cells = (size_t)a.ex * a.ey * a.ez;
+    const size_t smem = head + cells * sizeof(C);
     const int threads = (DIM == 3 && smem > 96 * 1024) ? 512 : 256;
     CFB_CUDA_OK(cudaFuncSetAttribute(interp_tile_kernel<T, DIM, NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
