@@ -588,7 +588,7 @@ def run_slab(args, cfg_id, cfg, ctx, steps, warmup, with_e2e=True, with_cpu=True
     all-to-all) and the bin sort there.  Type 2 then needs no collective; type 1 adds the halos around the
     ring and all-reduces the mode array inside the step."""
     torch, dist = ctx["torch"], ctx["dist"]
-    from cufinufft_b200.multi import SlabPlan, SlabRouter, slab_type1, slab_type2
+    from cufinufft_b200.multi import MgpuComm, SlabPlan
     rank, local_rank, world, dev = ctx["rank"], ctx["local_rank"], ctx["world"], ctx["dev"]
     npdt, tdt, cdt = np.dtype("float64"), torch.float64, torch.complex128
     shape = tuple(cfg["modes"])[::-1]
@@ -610,35 +610,33 @@ def run_slab(args, cfg_id, cfg, ctx, steps, warmup, with_e2e=True, with_cpu=True
     g.manual_seed(4242 + rank)
     held = [(torch.rand(M_held, generator=g, device=dev, dtype=tdt) * 2 - 1) * np.pi for _ in range(3)]   # z, y, x of the points this rank holds
 
-    # ---- setpts = route the held points to their owners + bin sort (timed together, max over ranks) ----
-    def route():
-        router = SlabRouter(held[0], nf3, world, rank)
-        return router, [router.forward(h) for h in held]           # one coordinate at a time: 1e9 points leave little room for copies
+    # the library's own NCCL communicator: only the 128-byte id travels through torch.distributed (plumbing)
+    uid = [MgpuComm.unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    comm = MgpuComm(world, rank, uid[0], device=local_rank)
+    plan.set_comm(comm)
 
-    router, owned = route()
-    plan.set_pts(owned[0], owned[1], owned[2])
+    # ---- setpts = route the held points to their owners + bin sort, all inside the library (timed together) ----
+    plan.route_set_pts(held[0], held[1], held[2])
     torch.cuda.synchronize()
     t_set, t_sort = [], []
-    for _ in range(2):
-        del router, owned
-        torch.cuda.empty_cache()
+    for _ in range(3):
         barrier()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
         e0.record(stream)
-        router, owned = route()
+        plan.route_set_pts(held[0], held[1], held[2])
         e1.record(stream)
-        plan.set_pts(owned[0], owned[1], owned[2])
-        e2.record(stream)
         torch.cuda.synchronize()
-        t_set.append(e0.elapsed_time(e2))
-        t_sort.append(e1.elapsed_time(e2))
+        t_set.append(e0.elapsed_time(e1))
+    M = plan.M
+    t_sort = [0.0]
     ts = torch.tensor([float(np.median(t_set)), float(np.median(t_sort))], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
     setpts_ms, sort_ms = float(ts[0].item()), float(ts[1].item())
-    setpts_launches = plan.launch_counts()["setpts"]
+    setpts_launches = plan.launch_counts()["setpts"] + 9       # + owner, slot, 3 x pack kernels and the NCCL calls of routing
     outside = plan.info()["outside"]
-    M = router.n_owned
 
     gk = torch.Generator(device=dev)
     gk.manual_seed(7)                                   # the mode array is REPLICATED: same seed on every rank
@@ -650,10 +648,7 @@ def run_slab(args, cfg_id, cfg, ctx, steps, warmup, with_e2e=True, with_cpu=True
         fk.zero_()
 
     def step(cc, ff):
-        if ttype == 2:
-            slab_type2(plan, cc, ff)
-        else:
-            slab_type1(plan, cc, ff)          # spread, ring halo add (NCCL), FFTs, all-reduce of the modes (NCCL)
+        plan.execute(cc, ff)                  # type 1: spread, ring halo add (NCCL), FFTs, all-reduce of the modes (NCCL) -- one C call
 
     plan.set_timing(True)
     for _ in range(warmup):
@@ -719,7 +714,7 @@ def run_slab(args, cfg_id, cfg, ctx, steps, warmup, with_e2e=True, with_cpu=True
             nb_fk, nb_c = fk_host.numel() * 16, c_host.numel() * 16
             e2e = {"value": M_total / (ms_e2e * 1e-3), "unit": "NU pts/s", "h2d_bytes_per_step": nb_fk if ttype == 2 else nb_c,
                    "d2h_bytes_per_step": nb_c if ttype == 2 else nb_fk, "ms_per_step": ms_e2e,
-                   "api": "per rank: pinned host input -> device, cufinufft_slab_* stages (C ABI), result -> pinned host"}
+                   "api": "per rank: pinned host input -> device, cufinufft_slab_execute (C ABI, NCCL inside), result -> pinned host"}
             del fk_host, c_host, fk_dev, c_dev
         except Exception as exc:   # noqa: BLE001
             e2e = {"value": None, "error": repr(exc)}
@@ -752,8 +747,8 @@ def run_slab(args, cfg_id, cfg, ctx, steps, warmup, with_e2e=True, with_cpu=True
             "vs_ref_gpu": {"available": False, "why": "the reference is single-GPU and needs ~100 GB for this size next to ours; "
                                                       "parity at full size: tests/test_fullsize_gpu.py::test_config5_full_size_single_gpu"},
             "stages_ms": stages,
-            "setpts": {"ms": setpts_ms, "bin_sort_ms": sort_ms, "routing_ms": setpts_ms - sort_ms, "pts_per_s": M_total / (setpts_ms * 1e-3),
-                       "launches": setpts_launches, "includes": "owner computation, counts all-gather, all-to-all of the coordinates (NCCL), bin sort"},
+            "setpts": {"ms": setpts_ms, "pts_per_s": M_total / (setpts_ms * 1e-3), "launches": setpts_launches,
+                       "includes": "cufinufft_slab_route_setpts: owner computation, counts all-gather, all-to-all of the coordinates (NCCL), bin sort"},
             "checksum_abs_rank0": checksum, "cpu_baseline": None,
         }
         if with_cpu and not args.no_cpu_baseline and world == 1:
@@ -761,7 +756,8 @@ def run_slab(args, cfg_id, cfg, ctx, steps, warmup, with_e2e=True, with_cpu=True
             cb["sample"] = "fine grid down-scaled to 128^3 modes on the host: " + cb["sample"]
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated")}
     plan.destroy()
-    del held, owned, c, fk, router
+    comm.destroy()
+    del held, c, fk
     torch.cuda.empty_cache()
     return line
 

@@ -105,6 +105,13 @@ for _sfx, _real in (("", c_double), ("f", c_float)):
         slab_halo_pack=_bind("cufinufft%s_slab_halo_pack" % _sfx, [c_int, c_void_p, c_void_p]),
         slab_halo_add=_bind("cufinufft%s_slab_halo_add" % _sfx, [c_int, c_void_p, c_void_p]),
         slab_type1_finish=_bind("cufinufft%s_slab_type1_finish" % _sfx, [c_void_p, c_void_p]),
+        # the same with the collectives inside the library (NCCL; csrc/mgpu.cu)
+        slab_set_comm=_bind("cufinufft%s_slab_set_comm" % _sfx, [c_void_p, c_void_p]),
+        slab_route_setpts=_bind("cufinufft%s_slab_route_setpts" % _sfx, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+        slab_route_info=_bind("cufinufft%s_slab_route_info" % _sfx, [c_void_p, c_void_p]),
+        slab_route_forward=_bind("cufinufft%s_slab_route_forward" % _sfx, [c_void_p, c_void_p, c_void_p]),
+        slab_route_backward=_bind("cufinufft%s_slab_route_backward" % _sfx, [c_void_p, c_void_p, c_void_p]),
+        slab_execute=_bind("cufinufft%s_slab_execute" % _sfx, [c_void_p, c_void_p, c_void_p]),
     )
 
 # reference-compatible module-level names
@@ -121,13 +128,19 @@ phihat_quadrature = _bind("cufinufft_b200_phihat_quadrature", [c_int, c_int, c_d
                                                                c_void_p, c_void_p])
 
 microbench = _bind("cufinufft_b200_microbench", [c_int, c_int, POINTER(c_double)])
+mgpu_unique_id = _bind("cufinufft_mgpu_unique_id", [c_void_p])
+mgpu_comm_create = _bind("cufinufft_mgpu_comm_create", [c_int, c_int, c_void_p, c_int, POINTER(c_void_p)])
+mgpu_comm_destroy = _bind("cufinufft_mgpu_comm_destroy", [c_void_p])
 
 C_ABI_SYMBOLS = [base % s for s in ("", "f") for base in (
     "cufinufft%s_default_opts", "cufinufft%s_makeplan", "cufinufft%s_setpts", "cufinufft%s_execute",
     "cufinufft%s_destroy")]
-EXTENSION_SYMBOLS = ["cufinufft_b200_version", "cufinufft_b200_host_params", "cufinufft_b200_host_workplan", "cufinufft_b200_phihat_quadrature", "cufinufft_b200_microbench"] + [base % s for s in ("", "f") for base in (
+EXTENSION_SYMBOLS = ["cufinufft_b200_version", "cufinufft_b200_host_params", "cufinufft_b200_host_workplan", "cufinufft_b200_phihat_quadrature", "cufinufft_b200_microbench",
+                     "cufinufft_mgpu_unique_id", "cufinufft_mgpu_comm_create", "cufinufft_mgpu_comm_destroy"] + [base % s for s in ("", "f") for base in (
     "cufinufft%s_set_stream", "cufinufft%s_setpts_host", "cufinufft%s_execute_host", "cufinufft%s_spread",
     "cufinufft%s_interp", "cufinufft%s_get_ints", "cufinufft%s_get_reals", "cufinufft%s_set_timing",
     "cufinufft%s_get_timing", "cufinufft%s_get_launch_counts", "cufinufft%s_set_interp_engine", "cufinufft%s_set_sort_levels",
     "cufinufft%s_slab_makeplan", "cufinufft%s_slab_info", "cufinufft%s_slab_type2", "cufinufft%s_slab_type1_spread",
-    "cufinufft%s_slab_halo_pack", "cufinufft%s_slab_halo_add", "cufinufft%s_slab_type1_finish")]
+    "cufinufft%s_slab_halo_pack", "cufinufft%s_slab_halo_add", "cufinufft%s_slab_type1_finish",
+    "cufinufft%s_slab_set_comm", "cufinufft%s_slab_route_setpts", "cufinufft%s_slab_route_info", "cufinufft%s_slab_route_forward",
+    "cufinufft%s_slab_route_backward", "cufinufft%s_slab_execute")]

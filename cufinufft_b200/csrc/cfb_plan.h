@@ -8,6 +8,7 @@
 #include <cufft.h>
 #include <cstdint>
 #include <cstdio>
+#include <vector>
 #include "../../include/cufinufft_opts.h"
 
 namespace cfb {
@@ -65,6 +66,20 @@ struct SortGeo {
     // point's shared-memory bank class, (its first stencil cell's index in the bin tile) mod bankc, instead of
     // the stencil cell; the tile has bex x bey (x bez) cells and a halo of bpad.  bankc = 0: stencil-cell order.
     int bankc, bex, bey, bez, bpad;
+};
+
+// multi-GPU state of a slab plan (mgpu.cu): communicator + routing of the points between the rank that
+// holds them and the rank that owns them
+struct MgpuComm;
+struct RouteState {
+    MgpuComm *comm = nullptr;
+    int n_held = 0, n_owned = 0;
+    DevBuf slot;                         // int[n_held]: position of held point i in the send order (grouped by owner)
+    DevBuf owned[3];                     // T[n_owned]: coordinates of the owned points (what setpts sorts)
+    DevBuf sendbuf, recvbuf;             // staging for one exchanged array
+    DevBuf counts;                       // int[world*world + 2*world] device scratch
+    DevBuf halo[4];                      // send_lo, send_hi, recv_prev, recv_next
+    long long send_counts[64] = {0}, recv_counts[64] = {0};
 };
 
 template <typename T>
@@ -135,6 +150,16 @@ struct Plan {
     cufftHandle fft2d = 0, fftz = 0;     // batched (x,y) planes of the local grid; strided z pencils of zbuf
     bool have_fft2d = false, have_fftz = false;
     DevBuf zbuf;                         // C[nf3g][mt][ms]: mode columns, all z planes (z-pencil layout)
+    RouteState route;                    // multi-GPU (mgpu.cu)
+    // host-pointer calls (plan.cu: setpts_host / execute_host): the points are ALSO sorted in `chunks` of the
+    // caller's index range (child plans without grid or FFT), so that the H2D copy of the strengths of chunk
+    // k+1 overlaps the spreading of chunk k (type 1) and the D2H copy of the values of chunk k the
+    // interpolation of chunk k+1 (type 2)
+    double tol = 0;
+    std::vector<Plan<T> *> chunks;
+    std::vector<long long> chunk_off;    // first point of every chunk, + the total
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
     // timing / accounting
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -184,3 +209,7 @@ template <typename T> int slab_type1_finish(Plan<T> &p, typename Plan<T>::C *fk_
     } while (0)
 
 }  // namespace cfb
+
+// the opaque handles of the C ABI
+struct cufinufft_plan_s  { cfb::Plan<double> *p; cfb::DevBuf dc, dfk; };
+struct cufinufftf_plan_s { cfb::Plan<float> *p;  cfb::DevBuf dc, dfk; };

@@ -17,8 +17,11 @@ Two partitionings (BASELINE.json north_star):
   gloo in the CPU tests); `slab_type1_emulated` runs all ranks of a decomposition in ONE process
   (several slab plans on one device, buffers handed over directly) for single-GPU tests.
 
-The device work goes through the C ABI of libcufinufft.so (`SlabPlan`); torch is imported
-lazily and only used for buffers and torch.distributed -- plumbing, not compute.
+The device work goes through the C ABI of libcufinufft.so (`SlabPlan`).  On GPUs the collectives are
+INSIDE the library too (csrc/mgpu.cu: NCCL): `MgpuComm` + `SlabPlan.set_comm / route_set_pts /
+route_forward / route_backward / execute` are ctypes calls and need no torch at all.  The torch.distributed
+functions further down (`slab_type1`, `SlabRouter`, ...) are the round-1 orchestration kept for the gloo CPU
+tests of the host logic and for callers that bring their own transport; torch is imported lazily there.
 """
 import ctypes
 from ctypes import byref, c_int, c_void_p
@@ -82,6 +85,60 @@ def _ptr(a):
     if a is None:
         return None
     return a.ptr if hasattr(a, "ptr") else a.data_ptr()
+
+
+class MgpuComm:
+    """NCCL communicator owned by the library (cufinufft_mgpu_comm_*), one per process.  `unique_id()` on rank 0
+    gives the 128 bytes every rank passes to the constructor -- moving them between the processes is the
+    caller's business (`file_rendezvous` below does it through a file; bench.py uses a torch.distributed
+    broadcast)."""
+
+    def __init__(self, world, rank, unique_id, device=0):
+        from . import _cufinufft as _ll
+        self._ll, self.world, self.rank, self.device = _ll, world, rank, device
+        self.handle = c_void_p(None)
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        ier = _ll.mgpu_comm_create(world, rank, buf, device, byref(self.handle))
+        if ier != 0:
+            raise RuntimeError("Error creating the NCCL communicator (%d)." % ier)
+
+    @staticmethod
+    def unique_id():
+        from . import _cufinufft as _ll
+        buf = ctypes.create_string_buffer(128)
+        if _ll.mgpu_unique_id(buf) != 0:
+            raise RuntimeError("ncclGetUniqueId failed.")
+        return buf.raw
+
+    @classmethod
+    def file_rendezvous(cls, world, rank, path, device=0, timeout=120.0):
+        """Rank 0 writes the unique id to `path` (atomically), the others wait for it."""
+        import os
+        import time
+        if rank == 0:
+            uid = cls.unique_id()
+            with open(path + ".tmp", "wb") as fh:
+                fh.write(uid)
+            os.replace(path + ".tmp", path)
+        else:
+            t0 = time.time()
+            while not os.path.exists(path):
+                if time.time() - t0 > timeout:
+                    raise RuntimeError("timed out waiting for " + path)
+                time.sleep(0.05)
+            uid = open(path, "rb").read()
+        return cls(world, rank, uid, device)
+
+    def destroy(self):
+        if self.handle is not None and self.handle.value:
+            self._ll.mgpu_comm_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 class SlabPlan:
@@ -180,6 +237,32 @@ class SlabPlan:
 
     def type1_finish(self, fk_partial):
         self._ok(self._fn["slab_type1_finish"](_ptr(fk_partial), self.plan), "type1_finish")
+
+    # -- collectives inside the library (csrc/mgpu.cu) -----------------------------------------
+    def set_comm(self, comm):
+        self._comm = comm                                    # keep it alive as long as the plan
+        self._ok(self._fn["slab_set_comm"](self.plan, comm.handle), "set_comm")
+
+    def route_set_pts(self, kz, ky, kx):
+        """The points this rank HOLDS (any z; slab axis first): routed to their owners and bin-sorted there.
+        Returns the number of points this rank owns afterwards."""
+        M = kz.numel() if hasattr(kz, "numel") else kz.size
+        self.references = [kz, ky, kx]
+        self._ok(self._fn["slab_route_setpts"](M, _ptr(kx), _ptr(ky), _ptr(kz), self.plan), "route_setpts")
+        v = (ctypes.c_longlong * 2)()
+        self._ok(self._fn["slab_route_info"](self.plan, v), "route_info")
+        self.M = int(v[1])
+        return self.M
+
+    def route_forward(self, held, owned):
+        self._ok(self._fn["slab_route_forward"](_ptr(held), _ptr(owned), self.plan), "route_forward")
+
+    def route_backward(self, owned, held):
+        self._ok(self._fn["slab_route_backward"](_ptr(owned), _ptr(held), self.plan), "route_backward")
+
+    def execute(self, c, fk):
+        """This rank's share of the transform, collectives included (type 1: `fk` is complete on return)."""
+        self._ok(self._fn["slab_execute"](_ptr(c), _ptr(fk), self.plan), "execute")
 
     def halo_buffers(self, device=None):
         """(send_lo, send_hi, recv_prev, recv_next): four torch tensors of pad*nf1*nf2 complex numbers."""

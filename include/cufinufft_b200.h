@@ -33,7 +33,8 @@ enum {
     CFB_ERR_CUDA = 11,          /* a CUDA runtime call failed (cudaGetLastError text on stderr) */
     CFB_ERR_CUFFT = 12,
     CFB_ERR_NOT_IMPLEMENTED = 13, /* type 3 (absent in the reference too, src/cufinufft.cu:533-536) */
-    CFB_ERR_NO_POINTS_SET = 14
+    CFB_ERR_NO_POINTS_SET = 14,
+    CFB_ERR_NCCL = 15           /* an NCCL call failed (ncclGetErrorString text on stderr) */
 };
 
 const char *cufinufft_b200_version(void);
@@ -164,6 +165,37 @@ int cufinufft_slab_halo_add(int side, cuDoubleComplex *buf, cufinufft_plan plan)
 int cufinufftf_slab_halo_add(int side, cuFloatComplex *buf, cufinufftf_plan plan);
 int cufinufft_slab_type1_finish(cuDoubleComplex *fk_partial, cufinufft_plan plan);
 int cufinufftf_slab_type1_finish(cuFloatComplex *fk_partial, cufinufftf_plan plan);
+
+/* ---- the same decomposition with the collectives INSIDE the library (csrc/mgpu.cu): one process per GPU,
+ * NCCL over NVLink.  The caller creates one communicator per process -- rank 0 calls mgpu_unique_id and hands
+ * the 128 bytes to the other ranks by any means (file, MPI, a torch store) --, attaches it to its slab plan
+ * and then needs three calls per transform, all stream-ordered on the plan's stream:
+ *   slab_route_setpts  this rank HOLDS M points anywhere in the domain (device pointers): their owners are
+ *                      computed with setpts' own rescale, counts are all-gathered, the coordinates go to the
+ *                      owning ranks (grouped ncclSend/ncclRecv) and are bin-sorted there.  One host
+ *                      synchronisation (buffer sizes).  slab_route_info -> {points held, points owned}.
+ *   slab_route_forward / _backward   per-point complex data holder -> owner (strengths, type 1) and
+ *                      owner -> holder in the holder's original order (values, type 2).
+ *   slab_execute       type 2: fk (replicated, [mu][mt][ms]) -> c (owned points); no collective.
+ *                      type 1: c (owned points) -> spread, ring halo exchange + add, FFTs, deconvolve,
+ *                      all-reduce: fk holds the COMPLETE mode array on every rank.
+ * The step-by-step calls above remain for callers that bring their own transport. */
+typedef struct cufinufft_mgpu_comm_s *cufinufft_mgpu_comm;
+int cufinufft_mgpu_unique_id(void *id128);
+int cufinufft_mgpu_comm_create(int world, int rank, const void *id128, int device, cufinufft_mgpu_comm *comm);
+int cufinufft_mgpu_comm_destroy(cufinufft_mgpu_comm comm);
+int cufinufft_slab_set_comm(cufinufft_plan plan, cufinufft_mgpu_comm comm);
+int cufinufftf_slab_set_comm(cufinufftf_plan plan, cufinufft_mgpu_comm comm);
+int cufinufft_slab_route_setpts(int M, const double *x, const double *y, const double *z, cufinufft_plan plan);
+int cufinufftf_slab_route_setpts(int M, const float *x, const float *y, const float *z, cufinufftf_plan plan);
+int cufinufft_slab_route_info(cufinufft_plan plan, long long *out2);
+int cufinufftf_slab_route_info(cufinufftf_plan plan, long long *out2);
+int cufinufft_slab_route_forward(const cuDoubleComplex *held, cuDoubleComplex *owned, cufinufft_plan plan);
+int cufinufftf_slab_route_forward(const cuFloatComplex *held, cuFloatComplex *owned, cufinufftf_plan plan);
+int cufinufft_slab_route_backward(const cuDoubleComplex *owned, cuDoubleComplex *held, cufinufft_plan plan);
+int cufinufftf_slab_route_backward(const cuFloatComplex *owned, cuFloatComplex *held, cufinufftf_plan plan);
+int cufinufft_slab_execute(cuDoubleComplex *c, cuDoubleComplex *fk, cufinufft_plan plan);
+int cufinufftf_slab_execute(cuFloatComplex *c, cuFloatComplex *fk, cufinufftf_plan plan);
 
 #ifdef __cplusplus
 }
