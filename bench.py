@@ -435,6 +435,8 @@ def run_plain(args, cfg_id, cfg, ctx, steps, warmup, with_e2e=True, with_cpu=Tru
     opts = dict(cfg["opts"], gpu_device_id=local_rank)
     plan = cufinufft(cfg["type"], shape, n_trans=ntransf, eps=cfg["tol"], dtype=npdt, maxbatch=cfg.get("maxbatch", 1), **opts)
     plan.set_stream(stream.cuda_stream)
+    if args.sort_levels:
+        plan.set_sort_levels(args.sort_levels)
     geo = plan.geometry()
     cfg["nf"] = [geo["nf1"], geo["nf2"], geo["nf3"]][:dim]
 
@@ -783,6 +785,7 @@ def main():
     ap.add_argument("--no-ref", action="store_true", help="skip timing the reference GPU library beside ours")
     ap.add_argument("--no-extra", action="store_true", help="headline workload only")
     ap.add_argument("--scale", type=float, default=1.0, help="scale M (debug)")
+    ap.add_argument("--sort-levels", type=int, default=0, help="cufinufft_set_sort_levels value (experiments: +4 no coarse partition, +8 always)")
     ap.add_argument("--opt", action="append", default=[], help="override a cufinufft_opts field, e.g. --opt gpu_binsizex=8 (experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -51,6 +51,10 @@ struct SortGeo {
     // reference bin and dimension; internal bin = refbin * spbt + sub, so the reference's bin-major
     // order is kept and its arrays are sums over groups of spbt internal bins
     int ibs[3], spb[3], spbt;
+    // power-of-two bin sizes (the defaults: 32x32, 16x16x2): lg_ibs >= 0, and every division of the key is an
+    // exact scaling by inv_ibs = 1 / ibs -- same integers as the divisions, a third of the instructions
+    int lg_ibs[3], lg_spb[3];
+    float inv_ibs[3];
     // stencil-origin cells per internal bin and dimension (the "fine" part of the order).  Either
     // they are part of the global key (nk = nkf, cpb = cpbf) or the global key is the bin alone
     // (nk = 1, cpb = 1) and every work item is sorted by cell afterwards (local_sort_kernel)
@@ -112,12 +116,18 @@ struct Plan {
     int M = -1;
     const T *kx = nullptr, *ky = nullptr, *kz = nullptr;
     DevBuf recs;                         // PtRec<T>[M], sorted by (bin, stencil cell)
-    DevBuf sortidx, idxnupts;            // int[M]: rank of a point inside its key; inverse permutation (on demand)
-    DevBuf keyoff, tilesum;              // int[nkeys+1] key histogram -> offsets; scan scratch
+    DevBuf idxnupts;                     // int[M]: inverse permutation (materialised on demand)
+    DevBuf keyoff, tilesum;              // int[4 + nkeys + 1] key histogram -> offsets -> cursors (setpts.cu); scan scratch
+    const int *key_offsets() const { return keyoff.as<int>() + 3; }   // [k] = first sorted point of key k, [nkeys] = M (after setpts)
     SortGeo sortgeo;
     bool fine_sort_allowed = true;
     bool local_sort = false;             // two-level order: bins globally, stencil cells per work item
     int sort_levels = 0;                 // 0 automatic, 1 / 2 forced (cufinufft*_set_sort_levels: tests, A/B)
+    int sort_partition = 0;              // coarse partition in front of the counting sort: 0 automatic, 1 never, 2 always
+    long long sort_bucket_bytes = 4LL << 20;    // records per coarse bucket (bytes): a window L2 holds several of
+    bool key_generic = false;            // force the generic key code (tests: cufinufft*_set_sort_levels + 16)
+    bool partitioned = false;            // ... used by the last setpts
+    DevBuf tmprecs, coarse;              // PtRec<T>[M] in coarse-bucket order; int[<= 4097] bucket counts / cursors
     bool idx_valid = false;
     DevBuf binsize, binstartpts, numsubprob, subprobstartpts, subprob_to_bin;
     DevBuf scalars;                      // int[8]: [0] totalnumsubprob, [1] work counter, ...

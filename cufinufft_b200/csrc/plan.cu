@@ -89,9 +89,9 @@ static void free_plan(Plan<T> *p)
     if (p->have_fft2d) cufftDestroy(p->fft2d);
     if (p->have_fftz) cufftDestroy(p->fftz);
     p->zbuf.release();
-    for (DevBuf *b : {&p->recs, &p->keyoff, &p->tilesum, &p->sortidx, &p->idxnupts, &p->binsize, &p->binstartpts, &p->numsubprob,
+    for (DevBuf *b : {&p->recs, &p->keyoff, &p->tilesum, &p->idxnupts, &p->binsize, &p->binstartpts, &p->numsubprob,
                       &p->subprobstartpts, &p->subprob_to_bin, &p->isubstart, &p->is2b, &p->scalars, &p->fw, &p->fwker[0], &p->fwker[1],
-                      &p->fwker[2], &p->hostside, &p->hcoef, &p->route.slot, &p->route.owned[0], &p->route.owned[1], &p->route.owned[2],
+                      &p->fwker[2], &p->hostside, &p->hcoef, &p->tmprecs, &p->coarse, &p->route.slot, &p->route.owned[0], &p->route.owned[1], &p->route.owned[2],
                       &p->route.sendbuf, &p->route.recvbuf, &p->route.counts, &p->route.halo[0], &p->route.halo[1], &p->route.halo[2],
                       &p->route.halo[3]})
         b->release();
@@ -701,8 +701,8 @@ int cufinufft_get_timing(cufinufft_plan plan, float *out) { return cfb::get_timi
 int cufinufftf_get_timing(cufinufftf_plan plan, float *out) { return cfb::get_timing<float>(PD(plan), out); }
 int cufinufft_set_interp_engine(cufinufft_plan plan, int e) { if (!PD(plan) || e < 0 || e > 2) return CFB_ERR_BAD_ARG; plan->p->interp_engine = e; return 0; }
 int cufinufftf_set_interp_engine(cufinufftf_plan plan, int e) { if (!PD(plan) || e < 0 || e > 2) return CFB_ERR_BAD_ARG; plan->p->interp_engine = e; return 0; }
-int cufinufft_set_sort_levels(cufinufft_plan plan, int l) { if (!PD(plan) || l < 0 || l > 2) return CFB_ERR_BAD_ARG; plan->p->sort_levels = l; return 0; }
-int cufinufftf_set_sort_levels(cufinufftf_plan plan, int l) { if (!PD(plan) || l < 0 || l > 2) return CFB_ERR_BAD_ARG; plan->p->sort_levels = l; return 0; }
+int cufinufft_set_sort_levels(cufinufft_plan plan, int l) { if (!PD(plan) || l < 0 || (l & 3) > 2 || ((l >> 2) & 3) > 2 || l > 31) return CFB_ERR_BAD_ARG; plan->p->sort_levels = l & 3; plan->p->sort_partition = (l >> 2) & 3; plan->p->key_generic = (l & 16) != 0; return 0; }
+int cufinufftf_set_sort_levels(cufinufftf_plan plan, int l) { if (!PD(plan) || l < 0 || (l & 3) > 2 || ((l >> 2) & 3) > 2 || l > 31) return CFB_ERR_BAD_ARG; plan->p->sort_levels = l & 3; plan->p->sort_partition = (l >> 2) & 3; plan->p->key_generic = (l & 16) != 0; return 0; }
 int cufinufft_get_launch_counts(cufinufft_plan plan, int *o) { if (!PD(plan) || !o) return CFB_ERR_BAD_ARG; o[0] = plan->p->launches_setpts; o[1] = plan->p->launches_exec; return 0; }
 int cufinufftf_get_launch_counts(cufinufftf_plan plan, int *o) { if (!PD(plan) || !o) return CFB_ERR_BAD_ARG; o[0] = plan->p->launches_setpts; o[1] = plan->p->launches_exec; return 0; }
 

@@ -11,8 +11,10 @@
 //   idxnupts: a bin-major permutation (within-bin order is a race in the reference
 //   too, src/2d/spreadinterp2d.cu:120-121) --
 // with a different schedule, all stream-ordered with no host sync:
-//   K1 key_count     key = bin * cells_per_bin + stencil cell inside the bin; warp-aggregated
-//                    (match_any) histogram atomics return the rank of each point in its key
+//   K0 coarse_count / coarse_scatter   (only when the key table is far beyond L2) the points are first dealt
+//                    into a few hundred buckets = ranges of bin rows, so that K1 and K6 work in L2-sized windows
+//   K1 key_count     key = bin * cells_per_bin + stencil cell inside the bin; one reduction (no return
+//                    value) per distinct key of a warp into the key table
 //   K2 scan_reduce / scan_top / scan_apply   three-phase exclusive scan of the key counts
 //   K3 ref_bins     binsize[b] = off[(b+1)*cpb] - off[b*cpb], binstartpts[b] = off[b*cpb], integer
 //                    ceil-div subproblem counts
@@ -21,7 +23,8 @@
 //   K5 map_subprob   one thread per subproblem slot, binary search in subprobstartpts
 //   K6 place_points  ONE 16-byte (fp32) / 32-byte (fp64) record per point
 //                    {x_rescaled, y_rescaled, z_rescaled, original index} scattered to its sorted
-//                    slot: a single sector write per point instead of four, and the spread /
+//                    slot, which comes from the key's cursor (the scanned table entry, advanced by one
+//                    warp-aggregated atomic): a single sector write per point instead of four, and the spread /
 //                    interp kernels read it back with one coalesced vector load and never
 //                    re-evaluate RESCALE (the reference recomputes it 3x per point per execute).
 // Sorting INSIDE the bin by stencil cell (the reference leaves that order to a race) makes
@@ -29,7 +32,9 @@
 // keeping a run of such points in registers (spreadinterp.cuh).  The fine histogram is used
 // when it is not much larger than the point set (nkeys <= 8 M + 2^22), otherwise the key is
 // the bin alone.
-// Algorithmic bytes per point: K1 d*sF + 4, K6 d*sF + 4 + 4 + rec  (DESIGN.md).
+// Algorithmic bytes per point: K1 d*sF, K6 d*sF + rec; with K0: + d*sF + (d*sF + rec), K1 and K6 read rec instead
+// of d*sF.
+#include <cstdlib>
 #include "cfb_device.cuh"
 
 namespace cfb {
@@ -38,13 +43,26 @@ namespace cfb {
 template <typename T>
 __device__ __forceinline__ void dim_key(T xr, int d, const SortGeo &g, int &b, int &s, int &cell)
 {
-    b = bin_coord(xr, g.bs[d], g.nb[d]);
-    int origin = b * g.bs[d];
-    s = 0;
-    if (g.spb[d] > 1) {
-        s = (int)floor((xr - (T)origin) / (T)g.ibs[d]);
+    int origin;
+    if (g.lg_ibs[d] >= 0) {
+        // power-of-two sizes: q = internal-bin coordinate before the clamps; floor(x_r / bs) = q >> lg(spb) is the
+        // reference's own value (division by a power of two is exact), and so is the sub-bin (x_r - origin is exact)
+        const int q = (int)floor(xr * (T)g.inv_ibs[d]);
+        b = q >> g.lg_spb[d];
+        b = b >= g.nb[d] ? b - 1 : b;
+        b = b < 0 ? 0 : b;
+        s = q - (b << g.lg_spb[d]);
         s = s < 0 ? 0 : (s >= g.spb[d] ? g.spb[d] - 1 : s);
-        origin += s * g.ibs[d];
+        origin = ((b << g.lg_spb[d]) + s) << g.lg_ibs[d];
+    } else {
+        b = bin_coord(xr, g.bs[d], g.nb[d]);
+        origin = b * g.bs[d];
+        s = 0;
+        if (g.spb[d] > 1) {
+            s = (int)floor((xr - (T)origin) / (T)g.ibs[d]);
+            s = s < 0 ? 0 : (s >= g.spb[d] ? g.spb[d] - 1 : s);
+            origin += s * g.ibs[d];
+        }
     }
     if (g.bankc > 0) {
         // bank-class order: offset of the first stencil cell inside the bin's tile (origin - halo), clamped exactly
@@ -57,21 +75,14 @@ __device__ __forceinline__ void dim_key(T xr, int d, const SortGeo &g, int &b, i
     cell = g.nk[d] > 1 ? stencil_cell(xr, g.ns, origin, g.nk[d]) : 0;
 }
 
-// sort key = ((reference bin * sub-bins per bin + sub-bin) * cells per sub-bin + stencil cell)
-template <typename T, int DIM>
-__device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                                         int i, const SortGeo &g, T &xr, T &yr, T &zr, int *count_outside = nullptr)
+// RESCALE of one point (+ the slab clamp of z): what the point record keeps
+template <typename T, int DIM, bool WITH_X = true>
+__device__ __forceinline__ void rescale_point(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z, long long i,
+                                              const SortGeo &g, T &xr, T &yr, T &zr, int *count_outside = nullptr)
 {
-    int b, sb, c;
-    const int cs1 = g.bankc > 0 ? g.bex : g.nk[0], cs2 = g.bankc > 0 ? g.bex * g.bey : g.nk[0] * g.nk[1];   // cell strides
-    xr = rescale(x[i], g.nf[0]);
-    dim_key(xr, 0, g, b, sb, c);
-    int bin = b, sub = sb, cell = c;
-    if (DIM > 1) {
-        yr = rescale(y[i], g.nf[1]);
-        dim_key(yr, 1, g, b, sb, c);
-        bin += g.nb[0] * b; sub += g.spb[0] * sb; cell += cs1 * c;
-    }
+    xr = WITH_X ? rescale(x[i], g.nf[0]) : (T)0;
+    yr = 0; zr = 0;
+    if (DIM > 1) yr = rescale(y[i], g.nf[1]);
     if (DIM > 2) {
         zr = rescale(z[i], g.nfz);
         // slab plans: bins over the slab-local planes; the record keeps the GLOBAL z_r (weights are
@@ -79,30 +90,139 @@ __device__ __forceinline__ int point_key(const T *__restrict__ x, const T *__res
         // A point outside the slab (caller error) is pulled onto its edge and counted.  The stencil
         // of a point stays inside the halo for zl in [zlo - 1/2, zhi], so a caller whose own
         // rescale differs from ours in the last bit at a slab boundary is still served exactly.
-        T zl = zr - (T)g.zshift;
+        const T zl = zr - (T)g.zshift;
         if (zl < (T)g.zlo - (T)0.5 || zl > (T)g.zhi) {
             if (count_outside) atomicAdd(count_outside, 1);
             zr = zl < (T)g.zlo ? (T)(g.zlo + g.zshift) : (T)(g.zhi + g.zshift);
-            zl = zr - (T)g.zshift;
         }
-        dim_key(zl, 2, g, b, sb, c);
+    }
+}
+
+// sort key = ((reference bin * sub-bins per bin + sub-bin) * cells per sub-bin + stencil cell) of a rescaled point
+template <typename T, int DIM>
+__device__ __forceinline__ int key_of(T xr, T yr, T zr, const SortGeo &g)
+{
+    int b, sb, c;
+    const int cs1 = g.bankc > 0 ? g.bex : g.nk[0], cs2 = g.bankc > 0 ? g.bex * g.bey : g.nk[0] * g.nk[1];   // cell strides
+    dim_key(xr, 0, g, b, sb, c);
+    int bin = b, sub = sb, cell = c;
+    if (DIM > 1) {
+        dim_key(yr, 1, g, b, sb, c);
+        bin += g.nb[0] * b; sub += g.spb[0] * sb; cell += cs1 * c;
+    }
+    if (DIM > 2) {
+        dim_key(zr - (T)g.zshift, 2, g, b, sb, c);
         bin += g.nb[0] * g.nb[1] * b; sub += g.spb[0] * g.spb[1] * sb; cell += cs2 * c;
     }
     if (g.bankc > 0) cell &= g.bankc - 1;            // the bank class (bankc is a power of two)
     return (bin * g.spbt + sub) * g.cpb + cell;
 }
 
-// K1: histogram + rank.  Lanes of a warp that fall on the same key are aggregated into
-// one atomicAdd (clustered inputs put most of a warp on one key).
+// The same key, specialised at compile time for power-of-two bin sizes (the defaults) and for what the key holds
+// inside a bin: KM = 1 the bin alone, 2 the stencil cell, 3 the bank class.  The generic version above reads ~40
+// kernel parameters behind run-time branches -- 195 instructions per point, the constant loads alone kept the
+// address-divergence unit 90 % busy (profiles/r02n) -- this one needs ~90 and no branch.  KM = 0: generic.
+template <typename T, int KM>
+__device__ __forceinline__ void dim_key_p2(T xr, int d, const SortGeo &g, int &iq, int &cell)
+{
+    const int q = (int)floor(xr * (T)g.inv_ibs[d]);
+    int b = q >> g.lg_spb[d];
+    b = b >= g.nb[d] ? b - 1 : b;
+    b = b < 0 ? 0 : b;
+    int s = q - (b << g.lg_spb[d]);
+    s = s < 0 ? 0 : (s >= g.spb[d] ? g.spb[d] - 1 : s);
+    iq = (b << g.lg_spb[d]) + s;                       // internal-bin coordinate; b = iq >> lg_spb, s = iq & (spb - 1)
+    cell = 0;
+    if (KM == 2) {
+        int k = stencil_start(xr, g.ns) - ((iq << g.lg_ibs[d]) - g.ns / 2) - ((g.ns & 1) ? 0 : 1);
+        cell = k < 0 ? 0 : (k >= g.nk[d] ? g.nk[d] - 1 : k);
+    } else if (KM == 3) {
+        const int e = d == 0 ? g.bex : (d == 1 ? g.bey : g.bez);
+        const int o = stencil_start(xr, g.ns) - ((iq << g.lg_ibs[d]) - g.bpad);
+        cell = o < 0 ? 0 : (o > e - g.ns ? e - g.ns : o);
+    }
+}
+
+template <typename T, int DIM, int KM>
+__device__ __forceinline__ int key_any(T xr, T yr, T zr, const SortGeo &g)
+{
+    if (KM == 0) return key_of<T, DIM>(xr, yr, zr, g);
+    int iq, c;
+    dim_key_p2<T, KM>(xr, 0, g, iq, c);
+    int bin = iq >> g.lg_spb[0], sub = iq & (g.spb[0] - 1), cell = c;
+    if (DIM > 1) {
+        dim_key_p2<T, KM>(yr, 1, g, iq, c);
+        bin += g.nb[0] * (iq >> g.lg_spb[1]); sub += g.spb[0] * (iq & (g.spb[1] - 1));
+        cell += (KM == 3 ? g.bex : g.nk[0]) * c;
+    }
+    if (DIM > 2) {
+        dim_key_p2<T, KM>(zr - (T)g.zshift, 2, g, iq, c);
+        bin += g.nb[0] * g.nb[1] * (iq >> g.lg_spb[2]); sub += g.spb[0] * g.spb[1] * (iq & (g.spb[2] - 1));
+        cell += (KM == 3 ? g.bex * g.bey : g.nk[0] * g.nk[1]) * c;
+    }
+    if (KM == 1) return bin * g.spbt + sub;
+    if (KM == 3) cell &= g.bankc - 1;
+    return (bin * g.spbt + sub) * g.cpb + cell;
+}
+
+// One point of a setpts pass: from the caller's arrays (RESCALE here) or from the coarse-partitioned
+// records (already rescaled; `idx` = the caller's index).
+template <typename T, int DIM, bool FROM_RECS, int KM>
+__device__ __forceinline__ int fetch_point(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
+                                           const PtRec<T> *__restrict__ src, long long i, const SortGeo &g,
+                                           T &xr, T &yr, T &zr, int &idx, int *count_outside = nullptr)
+{
+    if (FROM_RECS) {
+        const PtRec<T> r = load_rec(src + i);
+        xr = r.x; yr = r.y; zr = r.z; idx = rec_index(r);
+    } else {
+        rescale_point<T, DIM>(x, y, z, i, g, xr, yr, zr, count_outside);
+        idx = (int)i;
+    }
+    return key_any<T, DIM, KM>(xr, yr, zr, g);
+}
+
+// Which lanes of the warp hold the same key?  MATCH.ANY answers in one instruction, but it runs on the address
+// divergence unit at ~2.5 cycles per lane -- as slow as the atomic it is meant to save (profiles/r02n: that unit
+// 80-90 % busy in every kernel that matched or reduced once per point).  Votes are cheap:
+//   peers_by_bits   exact peer mask of a key known to fit in `nbits` bits: one vote per bit
+//   peers_by_hash   lanes are grouped by the key's low five bits; each group's first lane is its leader and
+//                   the mask holds the lanes of the group whose key EQUALS the leader's.  A lane outside its
+//                   group's mask (another key with the same low bits) gets only itself.  Every lane is in
+//                   exactly one returned mask, equal keys of one group share it: enough to aggregate atomics.
+__device__ __forceinline__ unsigned peers_by_bits(int key, int nbits)
+{
+    unsigned m = 0xffffffffu;
+    for (int b = 0; b < nbits; ++b) {
+        const unsigned v = __ballot_sync(0xffffffffu, (key >> b) & 1);
+        m &= ((key >> b) & 1) ? v : ~v;
+    }
+    return m;
+}
+__device__ __forceinline__ unsigned peers_by_hash(int key, int lane)
+{
+    unsigned m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) {
+        const unsigned v = __ballot_sync(0xffffffffu, (key >> b) & 1);
+        m &= ((key >> b) & 1) ? v : ~v;
+    }
+    const int lead = __ffs(m) - 1;
+    const int kl = __shfl_sync(0xffffffffu, key, lead);
+    const unsigned same = __ballot_sync(0xffffffffu, key == kl) & m;       // lanes of my group that equal its leader
+    return key == kl ? same : (1u << lane);
+}
+
+// K1: histogram.  Lanes of a warp that fall on the same key are aggregated into one reduction
+// (clustered inputs put most of a warp on one key; same-address atomics serialise in L2).
 // Four points per thread and iteration: the twelve coordinate loads are in flight together, then the
-// four histogram atomics, then the four rank stores (one point per iteration left the kernel at the
-// latency of load -> atomic -> store chains: 1.7 TB/s with every table L2-resident, profiles/r01zi).
+// four histogram reductions (no return value: nothing waits for L2).
 constexpr int SP_UNROLL = 4;
 
-template <typename T, int DIM>
+template <typename T, int DIM, bool FROM_RECS, int KM>
 __global__ void __launch_bounds__(256)
-key_count_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                 const SortGeo g, int *__restrict__ keycnt, int *__restrict__ rank, int *__restrict__ outside)
+key_count_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z, const PtRec<T> *__restrict__ src,
+                 const SortGeo g, int *__restrict__ keycnt, int *__restrict__ outside)
 {
     const int lane = threadIdx.x & 31;
     const long long span = (long long)blockDim.x * SP_UNROLL;
@@ -112,19 +232,13 @@ key_count_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const 
         for (int u = 0; u < SP_UNROLL; ++u) {
             const long long i = base + (long long)u * blockDim.x + threadIdx.x;
             T xr, yr, zr;
-            k[u] = i < M ? point_key<T, DIM>(x, y, z, (int)i, g, xr, yr, zr, outside) : -1 - lane;
+            int idx;
+            k[u] = i < M ? fetch_point<T, DIM, FROM_RECS, KM>(x, y, z, src, i, g, xr, yr, zr, idx, outside) : -1 - lane;
         }
 #pragma unroll
         for (int u = 0; u < SP_UNROLL; ++u) {
-            const long long i = base + (long long)u * blockDim.x + threadIdx.x;
-            const bool valid = i < M;
-            const unsigned peers = __match_any_sync(0xffffffffu, k[u]);
-            const int leader = __ffs(peers) - 1;
-            const int rank_in_group = __popc(peers & ((1u << lane) - 1));
-            int basecnt = 0;
-            if (valid && lane == leader) basecnt = atomicAdd(&keycnt[k[u]], __popc(peers));
-            basecnt = __shfl_sync(0xffffffffu, basecnt, leader);
-            if (valid) rank[i] = basecnt + rank_in_group;
+            const unsigned peers = peers_by_hash(k[u], lane);
+            if (k[u] >= 0 && lane == __ffs(peers) - 1) atomicAdd(&keycnt[k[u]], __popc(peers));
         }
     }
 }
@@ -285,35 +399,192 @@ __device__ __forceinline__ void store_rec<double>(PtRec<double> *dst, double xr,
     d[1] = make_double2(zr, __longlong_as_double((long long)i));
 }
 
-// K6: scatter one record per point to its sorted slot (four points per thread and iteration:
-// coordinate and rank loads first, then the offset gathers, then the record stores).
-template <typename T, int DIM>
+// K6: scatter one record per point to its sorted slot.  The slot comes from the key's CURSOR: the scanned
+// table entry, advanced by one warp-aggregated atomic per distinct key of the warp (no rank array to write in
+// K1 and read back here; the order inside a key is the arrival order either way).  After this kernel entry k
+// of the table holds the END of key k = the start of key k + 1: readers use the table shifted by one entry
+// (Plan::key_offsets).  Four points per thread and iteration: loads, then the four atomics, then the stores.
+template <typename T, int DIM, bool FROM_RECS, int KM>
 __global__ void __launch_bounds__(256)
-place_points_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z,
-                    const SortGeo g, const int *__restrict__ keyoff, const int *__restrict__ rank,
-                    PtRec<T> *__restrict__ recs)
+place_points_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z, const PtRec<T> *__restrict__ src,
+                    const SortGeo g, int *__restrict__ cursor, PtRec<T> *__restrict__ recs)
 {
+    const int lane = threadIdx.x & 31;
     const long long span = (long long)blockDim.x * SP_UNROLL;
     for (long long base = (long long)blockIdx.x * span; base < M; base += (long long)gridDim.x * span) {
         T xr[SP_UNROLL], yr[SP_UNROLL], zr[SP_UNROLL];
-        int k[SP_UNROLL], rk[SP_UNROLL];
+        int k[SP_UNROLL], id[SP_UNROLL], pos[SP_UNROLL];
 #pragma unroll
         for (int u = 0; u < SP_UNROLL; ++u) {
             const long long i = base + (long long)u * blockDim.x + threadIdx.x;
-            xr[u] = 0; yr[u] = 0; zr[u] = 0; k[u] = 0; rk[u] = 0;
-            if (i < M) {
-                k[u] = point_key<T, DIM>(x, y, z, (int)i, g, xr[u], yr[u], zr[u]);
-                rk[u] = rank[i];
-            }
+            xr[u] = 0; yr[u] = 0; zr[u] = 0; k[u] = -1 - lane; id[u] = 0;
+            if (i < M) k[u] = fetch_point<T, DIM, FROM_RECS, KM>(x, y, z, src, i, g, xr[u], yr[u], zr[u], id[u]);
         }
-        int pos[SP_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SP_UNROLL; ++u) pos[u] = keyoff[k[u]] + rk[u];
 #pragma unroll
         for (int u = 0; u < SP_UNROLL; ++u) {
-            const long long i = base + (long long)u * blockDim.x + threadIdx.x;
-            if (i < M) store_rec<T>(recs + pos[u], xr[u], yr[u], zr[u], (int)i);
+            const unsigned peers = peers_by_hash(k[u], lane);
+            const int leader = __ffs(peers) - 1;
+            int b0 = 0;
+            if (k[u] >= 0 && lane == leader) b0 = atomicAdd(&cursor[k[u]], __popc(peers));
+            pos[u] = __shfl_sync(0xffffffffu, b0, leader) + __popc(peers & ((1u << lane) - 1));
         }
+#pragma unroll
+        for (int u = 0; u < SP_UNROLL; ++u)
+            if (k[u] >= 0) store_rec<T>(recs + pos[u], xr[u], yr[u], zr[u], id[u]);
+    }
+}
+
+// ---- coarse partition: the locality pass in front of the counting sort ---------------------------
+// The counting sort above scatters every point once -- histogram atomic, offset gather, record store -- at an
+// address that is random over the whole key table and the whole record array when the caller's points come in
+// random order.  Beyond L2 size that is one DRAM page miss and one read-modify-write of a half-written sector
+// per point (config 3: 5.2 ms for 1e8 16-byte records, 0.6 TB/s; profiles/r01y).  The remedy is to limit the
+// number of open write frontiers: the points are first dealt into <= CP_MAXB coarse buckets, contiguous ranges
+// of the SAME key (bucket = key >> kshift, a few MB of records each), and the counting sort then reads them in
+// that order, so that its atomics, gathers and record stores stay inside an L2-resident window which L2 merges
+// into full lines before they reach DRAM.
+//   coarse_count    histogram of the buckets in warp-private shared-memory counters (no atomics: the lanes of a warp
+//                   that share a bucket are found with match_any, their leader does a plain read-modify-write),
+//                   summed over the warps and added to the global counts once per block
+//   scan_top        exclusive scan of the <= 4097 bucket counts (cursors)
+//   coarse_scatter  tiles of CP_THREADS x CP_PPT points in registers, ranked the same way; the per-warp counts are
+//                   scanned per bucket, ONE cursor atomic per tile and bucket reserves the tile's run, and the
+//                   records {x_r, y_r, z_r, idx} go to cursor + warp offset + rank -- a few hundred open frontiers
+// What was measured on the way (config 3, profiles/r02j-k): ranking with one shared-memory atomic per point costs
+// 2 cycles per lane and pass (1.1 + 3.6 ms); global atomics on the few hundred bucket counters serialise at ~10
+// cycles each whatever the warp aggregation (16 ms per pass).
+// The bin arrays do not change (same histogram); only the within-key order does, which is a race in the
+// reference as well (setpts.cu header).
+constexpr int CP_MAXB = 1024;
+constexpr int CP_THREADS = 256;
+constexpr int CP_WARPS = CP_THREADS / 32;
+#ifndef CFB_CP_PPT
+#define CFB_CP_PPT 8
+#endif
+#ifndef CFB_CP_BPS
+#define CFB_CP_BPS 8
+#endif
+constexpr int CP_PPT = CFB_CP_PPT;     // points per thread and tile
+constexpr int CP_BPS = CFB_CP_BPS;     // blocks per SM of the two coarse kernels
+
+// rank of this lane's point among the points of its warp that went to bucket b so far (warp-private counters)
+__device__ __forceinline__ int warp_private_rank(int *wc, int b, int lane, int nbits)
+{
+    const unsigned peers = peers_by_bits(b, nbits);
+    const int leader = __ffs(peers) - 1;
+    int c = 0;
+    if (b >= 0 && lane == leader) { c = wc[b]; wc[b] = c + __popc(peers); }
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, c, leader) + __popc(peers & ((1u << lane) - 1));
+}
+
+// Bucket of a point: contiguous ranges of the sort key that are cheap to find.  The key is bin-major with x
+// fastest, so a ROW of reference bins along x (all sub-bins and stencil cells included) is a contiguous key range:
+// bucket = (by + nby * bz) >> kshift needs neither x nor the sub-bins nor the stencil cell -- a third of the key's
+// instructions, and the counting pass does not even load x.  1-D: bucket = reference bin >> kshift.
+template <typename T, int KM>
+__device__ __forceinline__ int ref_bin(T xr, int d, const SortGeo &g)
+{
+    if (KM == 0) return bin_coord(xr, g.bs[d], g.nb[d]);
+    int b = (int)floor(xr * (T)g.inv_ibs[d]) >> g.lg_spb[d];
+    b = b >= g.nb[d] ? b - 1 : b;
+    return b < 0 ? 0 : b;
+}
+template <typename T, int DIM, int KM, bool WITH_X>
+__device__ __forceinline__ int coarse_bucket(const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z, long long i,
+                                             const SortGeo &g, int kshift, T &xr, T &yr, T &zr, int *outside)
+{
+    rescale_point<T, DIM, WITH_X || DIM == 1>(x, y, z, i, g, xr, yr, zr, outside);
+    if (DIM == 1) return ref_bin<T, KM>(xr, 0, g) >> kshift;
+    int row = ref_bin<T, KM>(yr, 1, g);
+    if (DIM > 2) row += g.nb[1] * ref_bin<T, KM>(zr - (T)g.zshift, 2, g);
+    return row >> kshift;
+}
+
+// Both kernels give block `blk` the same contiguous range of tiles [blk * tpb, (blk + 1) * tpb): the count
+// kernel writes the block's bucket counts into the matrix cnt[bucket][block]; its exclusive scan (bucket-major) is,
+// for every block, where its points of every bucket start -- the scatter needs no global atomic at all (one cursor
+// atomic per tile and bucket was tried first: atomics WITH a return value on a few hundred addresses serialise at
+// ~100 ns each, 2.1 ms for config 3, profiles/r02s), and the order of the records is deterministic.
+template <typename T, int DIM, int KM>
+__global__ void __launch_bounds__(CP_THREADS)
+coarse_count_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z, const SortGeo g, int kshift,
+                    int nb, int nbits, long long tpb, int *__restrict__ cnt, int *__restrict__ outside)
+{
+    extern __shared__ int cp_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *wc = cp_smem + wid * nb;
+    for (int i = threadIdx.x; i < CP_WARPS * nb; i += CP_THREADS) cp_smem[i] = 0;
+    __syncthreads();
+    const long long tile = (long long)CP_THREADS * CP_PPT;
+    const long long p0 = (long long)blockIdx.x * tpb * tile;
+    const long long p1 = p0 + tpb * tile < M ? p0 + tpb * tile : M;
+    const long long span = (long long)CP_THREADS * SP_UNROLL;
+    for (long long base = p0; base < p1; base += span) {
+        int k[SP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SP_UNROLL; ++u) {
+            const long long i = base + (long long)u * CP_THREADS + threadIdx.x;
+            T xr, yr, zr;
+            k[u] = i < p1 ? coarse_bucket<T, DIM, KM, false>(x, y, z, i, g, kshift, xr, yr, zr, outside) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < SP_UNROLL; ++u) {
+            const unsigned peers = peers_by_bits(k[u], nbits);
+            if (k[u] >= 0 && lane == __ffs(peers) - 1) wc[k[u]] += __popc(peers);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += CP_THREADS) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < CP_WARPS; ++w) t += cp_smem[w * nb + b];
+        cnt[(size_t)b * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+template <typename T, int DIM, int KM>
+__global__ void __launch_bounds__(CP_THREADS)
+coarse_scatter_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, const T *__restrict__ z, const SortGeo g, int kshift,
+                      int nb, int nbits, long long tpb, const int *__restrict__ start, PtRec<T> *__restrict__ out)
+{
+    extern __shared__ int cp_smem[];                  // [CP_WARPS][nb] counts -> offsets, [nb] the tile's run starts, [nb] the block's cursors
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *wc = cp_smem + wid * nb, *runstart = cp_smem + CP_WARPS * nb, *cursor = runstart + nb;
+    for (int q = threadIdx.x; q < nb; q += CP_THREADS) cursor[q] = start[(size_t)q * gridDim.x + blockIdx.x];
+    const long long tile = (long long)CP_THREADS * CP_PPT;
+    const long long p0 = (long long)blockIdx.x * tpb * tile;
+    const long long p1 = p0 + tpb * tile < M ? p0 + tpb * tile : M;
+    for (long long base = p0; base < p1; base += tile) {
+        for (int i = threadIdx.x; i < CP_WARPS * nb; i += CP_THREADS) cp_smem[i] = 0;
+        __syncthreads();
+        T xr[CP_PPT], yr[CP_PPT], zr[CP_PPT];
+        int b[CP_PPT], r[CP_PPT];
+#pragma unroll
+        for (int u = 0; u < CP_PPT; ++u) {
+            // a warp takes 32 x CP_PPT CONSECUTIVE points: coalesced loads, and a rank that follows the input order
+            const long long i = base + (long long)wid * (32 * CP_PPT) + u * 32 + lane;
+            xr[u] = 0; yr[u] = 0; zr[u] = 0; b[u] = -1;
+            if (i < p1) b[u] = coarse_bucket<T, DIM, KM, true>(x, y, z, i, g, kshift, xr[u], yr[u], zr[u], nullptr);
+        }
+#pragma unroll
+        for (int u = 0; u < CP_PPT; ++u) r[u] = warp_private_rank(wc, b[u], lane, nbits);
+        __syncthreads();
+        for (int q = threadIdx.x; q < nb; q += CP_THREADS) {       // thread q owns bucket q's cursor in every tile
+            int t = 0;
+#pragma unroll
+            for (int w = 0; w < CP_WARPS; ++w) { const int c = cp_smem[w * nb + q]; cp_smem[w * nb + q] = t; t += c; }
+            const int c0 = cursor[q];
+            runstart[q] = c0; cursor[q] = c0 + t;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < CP_PPT; ++u) {
+            const long long i = base + (long long)wid * (32 * CP_PPT) + u * 32 + lane;
+            if (b[u] >= 0) store_rec<T>(out + (runstart[b[u]] + wc[b[u]] + r[u]), xr[u], yr[u], zr[u], (int)i);
+        }
+        __syncthreads();
     }
 }
 
@@ -326,8 +597,8 @@ trivial_order_kernel(int M, const T *__restrict__ x, const T *__restrict__ y, co
 {
     for (long long ii = (long long)blockIdx.x * blockDim.x + threadIdx.x; ii < M; ii += (long long)gridDim.x * blockDim.x) {
         int i = (int)ii;
-        T xr, yr = 0, zr = 0;
-        point_key<T, DIM>(x, y, z, i, g, xr, yr, zr, outside);      // rescale (+ slab clamp); key unused
+        T xr, yr, zr;
+        rescale_point<T, DIM>(x, y, z, i, g, xr, yr, zr, outside);  // rescale (+ slab clamp)
         store_rec<T>(recs + i, xr, yr, zr, i);
     }
 }
@@ -417,7 +688,7 @@ local_sort_kernel(const LocalSortArgs a, PtRec<T> *__restrict__ recs)
     }
 }
 
-template <typename T, int DIM>
+template <typename T, int DIM, int KM>
 static int setpts_dim(Plan<T> &p)
 {
     const int M = p.M;
@@ -429,8 +700,10 @@ static int setpts_dim(Plan<T> &p)
     int *substart = p.subprobstartpts.template as<int>();
     int *s2b = p.subprob_to_bin.template as<int>();
     int *scal = p.scalars.template as<int>();
-    int *rank = p.sortidx.template as<int>();
-    int *keyoff = p.keyoff.template as<int>();
+    // key table: counts -> exclusive offsets in entries [4, 4 + nkeys]; place_points advances them into end
+    // offsets, after which entry 3 + k is the start of key k again (entry 3 stays 0): Plan::key_offsets()
+    int *keybuf = p.keyoff.template as<int>();
+    int *keyoff = keybuf + 4;
     int *tilesum = p.tilesum.template as<int>();
     PtRec<T> *recs = p.recs.template as<PtRec<T>>();
     const int threads = 256;
@@ -451,9 +724,42 @@ static int setpts_dim(Plan<T> &p)
     const long long nkeys = (long long)p.nibins * g.cpb;
     const long long nscan = nkeys + 1;                       // trailing total
     const int ntiles = (int)((nscan + SCAN_TILE - 1) / SCAN_TILE);
-    CFB_CUDA_OK(cudaMemsetAsync(keyoff, 0, sizeof(int) * (size_t)nscan, st));
+    CFB_CUDA_OK(cudaMemsetAsync(keybuf, 0, sizeof(int) * (size_t)(nscan + 4), st));
+    // locality pass (see coarse_count_kernel): buckets of ~4 MB of records
+    const PtRec<T> *part = nullptr;
+    if (p.partitioned && M > 0) {
+        static const long long bucket_env = [] { const char *e = getenv("CFB_SORT_BUCKET_MB"); return e ? atoll(e) << 20 : 0LL; }();   // experiments
+        if (bucket_env > 0) p.sort_bucket_bytes = bucket_env;
+        int nb = 32;
+        while (nb < CP_MAXB && (long long)nb * p.sort_bucket_bytes < (long long)M * (long long)sizeof(PtRec<T>)) nb *= 2;
+        const long long nrows = DIM == 1 ? p.nbin[0] : (long long)p.nbin[1] * (DIM > 2 ? p.nbin[2] : 1);   // rows of bins along x
+        int kshift = 0;
+        while (((nrows - 1) >> kshift) >= nb) ++kshift;
+        nb = (int)((nrows - 1) >> kshift) + 1;
+        int *ccnt = p.coarse.template as<int>();
+        PtRec<T> *tmp = p.tmprecs.template as<PtRec<T>>();
+        int nbits = 1;                                   // votes per point: the bits of a bucket number + the validity bit
+        while ((1 << (nbits - 1)) < nb) ++nbits;
+        const size_t csm = (size_t)(CP_WARPS + 2) * nb * sizeof(int);
+        const long long tile = (long long)CP_THREADS * CP_PPT;
+        const long long wt = (M + tile - 1) / tile;
+        long long cb = wt < (long long)p.num_sms * CP_BPS ? wt : (long long)p.num_sms * CP_BPS;
+        const long long tpb = (wt + cb - 1) / cb;          // tiles per block
+        const int cblocks = (int)((wt + tpb - 1) / tpb);
+        const long long nmat = (long long)nb * cblocks + 1;   // count matrix [bucket][block] + the trailing total
+        const int mtiles = (int)((nmat + SCAN_TILE - 1) / SCAN_TILE);
+        CFB_CUDA_OK(cudaMemsetAsync(ccnt + nmat - 1, 0, sizeof(int), st));
+        coarse_count_kernel<T, DIM, KM><<<cblocks, CP_THREADS, csm, st>>>(M, x, y, z, g, kshift, nb, nbits, tpb, ccnt, p.slab ? scal + 3 : nullptr);
+        scan_reduce_kernel<<<mtiles, SCAN_THREADS, 0, st>>>(nmat, ccnt, tilesum);
+        scan_top_kernel<<<1, 1024, 0, st>>>(mtiles, tilesum);
+        scan_apply_kernel<<<mtiles, SCAN_THREADS, 0, st>>>(nmat, ccnt, tilesum);
+        coarse_scatter_kernel<T, DIM, KM><<<cblocks, CP_THREADS, csm, st>>>(M, x, y, z, g, kshift, nb, nbits, tpb, ccnt, tmp);
+        p.launches_setpts += 5;
+        part = tmp;
+    }
     if (M > 0) {
-        key_count_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, g, keyoff, rank, p.slab ? scal + 3 : nullptr);
+        if (part) key_count_kernel<T, DIM, true, KM><<<blocks, threads, 0, st>>>(M, x, y, z, part, g, keyoff, nullptr);
+        else key_count_kernel<T, DIM, false, KM><<<blocks, threads, 0, st>>>(M, x, y, z, nullptr, g, keyoff, p.slab ? scal + 3 : nullptr);
         p.launches_setpts++;
     }
     scan_reduce_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nscan, keyoff, tilesum);
@@ -488,12 +794,13 @@ static int setpts_dim(Plan<T> &p)
         p.launches_setpts += 5;
     }
     if (M > 0) {
-        place_points_kernel<T, DIM><<<blocks, threads, 0, st>>>(M, x, y, z, g, keyoff, rank, recs);
+        if (part) place_points_kernel<T, DIM, true, KM><<<blocks, threads, 0, st>>>(M, x, y, z, part, g, keyoff, recs);
+        else place_points_kernel<T, DIM, false, KM><<<blocks, threads, 0, st>>>(M, x, y, z, nullptr, g, keyoff, recs);
         p.launches_setpts++;
     }
     if (M > 0 && p.local_sort) {
         LocalSortArgs la;
-        la.keyoff = keyoff;
+        la.keyoff = p.key_offsets();
         la.s2b = p.ilist ? p.is2b.template as<int>() : s2b;
         la.substart = p.ilist ? p.isubstart.template as<int>() : substart;
         la.nsub = p.ilist ? p.isubstart.template as<int>() + p.nibins : scal;
@@ -527,6 +834,12 @@ int stage_setpts(Plan<T> &p)
         g.ibs[d] = p.ibs[d]; g.spb[d] = p.spb[d];
         g.nk[d] = g.nkf[d] = d < p.dim ? p.ibs[d] + (p.ns & 1) : 1;
         cpb *= g.nk[d];
+    }
+    for (int d = 0; d < 3; ++d) {
+        auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+        g.lg_ibs[d] = lg(g.ibs[d]); g.lg_spb[d] = lg(g.spb[d]);
+        if (g.lg_spb[d] < 0) g.lg_ibs[d] = -1;
+        g.inv_ibs[d] = g.lg_ibs[d] >= 0 ? 1.0f / (float)g.ibs[d] : 0.0f;
     }
     g.spbt = p.spb[0] * p.spb[1] * p.spb[2];
     g.cpbf = (int)(cpb < (1LL << 30) ? cpb : (1LL << 30));
@@ -562,10 +875,25 @@ int stage_setpts(Plan<T> &p)
     }
     g.cpb = (int)cpb;
     CFB_CUDA_OK(p.recs.reserve(M * sizeof(PtRec<T>)));
+    // locality pass in front of the counting sort (coarse_count / coarse_scatter): it costs an extra read of the
+    // coordinates and a read + write of the records, and pays when the one-level key table is far beyond L2 --
+    // then every histogram reduction and every cursor atomic of the direct sort is a DRAM sector read-modify-write
+    // (config 3: 537 MB table, setpts 8.2 -> 6.9 ms).  With an L2-resident table the direct scatter is faster
+    // (measured: config 2 2.5 vs 3.1 ms, config 5's density 7.0 vs 10.7 ms; profiles/r02v).
+    // cufinufft*_set_sort_levels: +4 never, +8 always.  It needs a second record array: when that does not
+    // fit next to everything else the direct scatter still works.
+    p.partitioned = p.sorted && p.M > 0 && p.sort_partition != 1 &&
+                    (p.sort_partition == 2 || (one_level && (nkeys + 1) * 4 >= 2 * p.l2_bytes && M * sizeof(PtRec<T>) >= (size_t)(4 * p.l2_bytes)));
+    if (p.partitioned) {
+        if (p.tmprecs.reserve(M * sizeof(PtRec<T>)) != cudaSuccess || p.coarse.reserve(((size_t)CP_MAXB * p.num_sms * CP_BPS + 8) * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            p.tmprecs.release();
+            p.partitioned = false;
+        }
+    }
     if (p.sorted) {
-        CFB_CUDA_OK(p.sortidx.reserve(M * sizeof(int)));
-        CFB_CUDA_OK(p.keyoff.reserve(((size_t)nkeys + 1 + 4) * sizeof(int)));
-        CFB_CUDA_OK(p.tilesum.reserve(((size_t)(nkeys + 1) / SCAN_TILE + 2) * sizeof(int)));
+        CFB_CUDA_OK(p.keyoff.reserve(((size_t)nkeys + 1 + 8) * sizeof(int)));
+        CFB_CUDA_OK(p.tilesum.reserve((((size_t)(nkeys + 1) + (size_t)CP_MAXB * p.num_sms * CP_BPS) / SCAN_TILE + 4) * sizeof(int)));
     }
     size_t maxslots = (size_t)p.nbins + M / (size_t)p.opts.gpu_maxsubprobsize + 1;
     CFB_CUDA_OK(p.subprob_to_bin.reserve(maxslots * sizeof(int)));
@@ -574,10 +902,24 @@ int stage_setpts(Plan<T> &p)
         CFB_CUDA_OK(p.is2b.reserve(((size_t)p.nibins + M / (size_t)p.imaxsub + 1) * sizeof(int)));
     }
     p.idx_valid = false;
-    switch (p.dim) {
-        case 1: return setpts_dim<T, 1>(p);
-        case 2: return setpts_dim<T, 2>(p);
-        default: return setpts_dim<T, 3>(p);
+    // compile-time specialisation of the key (key_any): power-of-two bin sizes in every dimension, and what the
+    // key holds inside a bin
+    int km = g.bankc > 0 ? 3 : (g.cpb == 1 ? 1 : 2);
+    for (int d = 0; d < p.dim; ++d) if (g.lg_ibs[d] < 0) km = 0;
+    if (p.key_generic) km = 0;
+    switch (p.dim * 4 + km) {
+        case 4: return setpts_dim<T, 1, 0>(p);
+        case 5: return setpts_dim<T, 1, 1>(p);
+        case 6: return setpts_dim<T, 1, 2>(p);
+        case 7: return setpts_dim<T, 1, 3>(p);
+        case 8: return setpts_dim<T, 2, 0>(p);
+        case 9: return setpts_dim<T, 2, 1>(p);
+        case 10: return setpts_dim<T, 2, 2>(p);
+        case 11: return setpts_dim<T, 2, 3>(p);
+        case 12: return setpts_dim<T, 3, 0>(p);
+        case 13: return setpts_dim<T, 3, 1>(p);
+        case 14: return setpts_dim<T, 3, 2>(p);
+        default: return setpts_dim<T, 3, 3>(p);
     }
 }
 

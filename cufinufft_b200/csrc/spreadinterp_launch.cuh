@@ -21,7 +21,7 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     a.recs = p.recs.template as<PtRec<T>>();
     a.c = nullptr; a.fw = nullptr;
     const bool split = p.ilist;                         // the engines' own work list (finer bins and/or larger items, setpts.cu)
-    a.keyoff = p.keyoff.template as<int>(); a.cpb = p.sortgeo.cpb;
+    a.keyoff = p.key_offsets(); a.cpb = p.sortgeo.cpb;
     a.s2b = split ? p.is2b.template as<int>() : p.subprob_to_bin.template as<int>();
     a.substart = split ? p.isubstart.template as<int>() : p.subprobstartpts.template as<int>();
     a.nsub = split ? p.isubstart.template as<int>() + p.nibins : p.scalars.template as<int>();

@@ -121,6 +121,9 @@ int cufinufftf_set_interp_engine(cufinufftf_plan plan, int engine);
 /* Order of the points inside a bin (takes effect at the next setpts): 0 = automatic, 1 = one level
  * (global histogram over (bin, stencil cell) keys), 2 = two levels (bins globally, stencil cells per
  * work item in shared memory -- chosen automatically when the one-level histogram would exceed 2 GB).
+ * Add 4 to switch the coarse-partition locality pass in front of the counting sort off, 8 to force it on
+ * (automatic: on once the point records outgrow a quarter of L2; csrc/setpts.cu: coarse_scatter_kernel).
+ * Add 16 to compute the sort keys with the generic code even for power-of-two bin sizes (csrc/setpts.cu: key_any).
  * Results do not depend on it; an A/B and test switch. */
 int cufinufft_set_sort_levels(cufinufft_plan plan, int levels);
 int cufinufftf_set_sort_levels(cufinufftf_plan plan, int levels);

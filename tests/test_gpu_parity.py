@@ -164,6 +164,27 @@ def test_two_level_point_order(case):
     assert plan.launch_counts()["setpts"] >= 9          # the local sort ran
 
 
+# The coarse partition in front of the counting sort (csrc/setpts.cu: coarse_count / coarse_scatter) switches itself
+# on only for point sets beyond a quarter of L2; forced here (sort_levels + 8) on small inputs of every kind, with
+# the one-level and the two-level order behind it, against the direct scatter (+ 4).  Same results (the order of
+# the points inside a key is free), same reference-facing bin arrays.
+@pytest.mark.parametrize("levels", [1, 2])
+@pytest.mark.parametrize("case", TWO_LEVEL_CASES, ids=lambda c: "t%d-%s-M%d-%s-%s" % (c[0], "x".join(map(str, c[1])), c[2], np.dtype(c[4]).name, c[5]))
+def test_coarse_partitioned_sort(case, levels):
+    nufft_type, modes, M, tol, dtype, dist, opts = case
+    dim = len(modes)
+    pts = make_points(M, dim, dtype, seed=92, dist=dist)
+    data = make_strengths(M, dtype) if nufft_type == 1 else make_modes_data(modes, dtype)
+    out, plan = gpu_nufft(nufft_type, modes, pts, data, tol, dtype, return_plan=True, sort_levels=8 + levels, **opts)
+    direct, plan0 = gpu_nufft(nufft_type, modes, pts, data, tol, dtype, return_plan=True, sort_levels=4 + levels, **opts)
+    slack = 4 if dist == "onebin" else 1                 # fp32 accumulation-order noise, see above
+    assert rel_l2(out[0], direct[0]) <= TOL_PARITY[dtype] * slack
+    ref = orc.nufft(nufft_type, modes, pts, data[0], tol, dtype=dtype)
+    assert rel_l2(out[0], ref) <= TOL_PARITY[dtype] * slack
+    _check_bins(plan, pts, dtype, opts.get("gpu_maxsubprobsize", 1024))
+    assert plan.launch_counts()["setpts"] == plan0.launch_counts()["setpts"] + 5      # count, 3-phase scan, scatter ran
+
+
 # Nonstandard upsampling factors (opts.upsampfac != 2: kernel width and beta from the cutoff formulas of
 # contrib/spreadinterp.cpp:43-62, fine grid sigma * modes; direct kernel evaluation only).  The reference
 # accepts them through the same opts field; sigma = 1.25 shrinks the fine grid of a 3-D transform 4x.
