@@ -339,8 +339,12 @@ static int setpts_host(Plan<T> *p, int M, const T *x, const T *y, const T *z)
         if (M > 0) CFB_CUDA_OK(cudaMemcpyAsync(d + (size_t)k * n, src[k], (size_t)M * sizeof(T), cudaMemcpyHostToDevice, p->stream));
     if (int e = setpts(p, M, d, d + n, d + 2 * n)) return e;
 
-    // type 1 loses run length when the points of a cell are dealt to several chunks: fewer chunks there
-    const int K = (M >= PIPE_MIN_POINTS && p->ntransf == 1 && !p->slab && !p->opts.gpu_spreadinterponly) ? (p->type == 1 ? 4 : 8) : 1;
+    // Type 1 pays for chunks: the spread kernels accumulate runs of points that share a stencil, and dealing the
+    // points of a cell to K chunks divides the run length by K.  2-D: 4 chunks still win (config 1: 2.11 -> 1.85 ms
+    // per host-buffer step); 3-D, where a run saves ns^3 tile updates, they lose (config 3, clustered: 26.8 -> 31.4 ms
+    // with 4 chunks; profiles/r02x) -- no chunks there.  Type 2 has no such coupling (config 2: 16.9 -> 14.2 ms).
+    const int K = (M >= PIPE_MIN_POINTS && p->ntransf == 1 && !p->slab && !p->opts.gpu_spreadinterponly)
+                      ? (p->type == 1 ? (p->dim <= 2 ? 4 : 1) : 8) : 1;
     if (K == 1) {
         for (Plan<T> *c : p->chunks) free_plan(c);
         p->chunks.clear();

@@ -5,6 +5,10 @@
 #include "spreadinterp.cuh"
 #include "spread_sm2.cuh"
 
+#ifndef CFB_TILE_PAD_PCT
+#define CFB_TILE_PAD_PCT 130
+#endif
+
 namespace cfb {
 
 template <typename T>
@@ -90,7 +94,7 @@ void plan_tile_geometry(Plan<T> &p)
     for (int sy = ex; sy < ex + 16; ++sy) {
         for (int rows = ey; rows < ey + (p.dim > 2 ? 16 : 1); ++rows) {
             long long cells = p.dim == 1 ? sy : (long long)sy * rows * ez;
-            if (cells * 10 > base_cells * 13 && !(sy == ex && rows == ey)) continue;   // <= 30 % padding
+            if (cells * 100 > base_cells * CFB_TILE_PAD_PCT && !(sy == ex && rows == ey)) continue;   // <= 30 % padding
             int cost = layout_cost(p.dim, p.ns, sy, sy * rows, cell);
             long long score = (long long)cost * 1000000 + cells;
             if (best_score < 0 || score < best_score) { best_score = score; best_sy = sy; best_rows = rows; best_cost = cost; }

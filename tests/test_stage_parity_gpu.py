@@ -142,6 +142,12 @@ HOST_CASES = [
     (1, (64, 64), 0, 1e-5, np.float32, 1, {}),               # no points at all: zeros out, nothing read
     (2, (64, 64), 0, 1e-5, np.float32, 1, {}),
     (1, (64, 48), 30_000, 1e-5, np.float32, 2, dict(gpu_spreadinterponly=1)),
+    # single transforms of >= 2e6 points take the chunked copy/compute pipeline of execute_host (csrc/plan.cu:
+    # PIPE_MIN_POINTS): 4 chunks of the caller's index range for type 1, 8 for type 2
+    (1, (256, 200), 2_500_000, 1e-5, np.float32, 1, {}),
+    (2, (256, 200), 2_500_000, 1e-9, np.float64, 1, {}),
+    (1, (48, 40, 36), 2_100_000, 1e-6, np.float64, 1, {}),
+    (2, (48, 40, 36), 2_100_003, 1e-5, np.float32, 1, {}),
 ]
 
 
