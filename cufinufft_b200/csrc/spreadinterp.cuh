@@ -62,6 +62,7 @@ struct SIArgs {
     int sy, sz, tile_cells;     // padded tile strides
     int horner, ncoef;
     int zshift;                 // slab plans: local plane = global plane - zshift (0 otherwise)
+    int zm, nb3, npairs;        // tile interpolation, 3-D: zm > 1 = one tile serves zm z-adjacent bins (npairs = nb1*nb2*ceil(nb3/zm) work items)
     int bankc;                  // > 0: the points of a bin are ordered by shared-memory bank class (cpb == bankc classes per bin)
     int thr_num, thr_den;       // tuning override of the short-run threshold (0 = built-in; env CFB_DIRECT_THR=num/den)
     T es_c, es_beta;
@@ -913,9 +914,13 @@ interp_tile_kernel(const SIArgs<T> a_in)
     stage_horner<T, NS>(a, s_hc);
 
     const int nsub = *a.nsub;
-    const long long total = (long long)nsub * a.nt;
+    // 3-D, wide fp64 stencils (one 130 KB tile per SM): a tile that serves ZM z-adjacent bins (bins are 2 planes
+    // thick, the halo 10) is loaded once for ZM x as many points -- config 5: 26 x 26 x 14 cells for two bins instead
+    // of 2 x (26 x 26 x 12), -16 % kernel time with the bin size doubled by hand (profiles/r03a).  The work item is
+    // then the bin GROUP; its member bins and their subproblems are walked inside the block.
+    const bool merged = DIM == 3 && a.zm > 1;
+    const long long total = merged ? (long long)a.npairs * a.nt : (long long)nsub * a.nt;
     const int ex = a.ex, ey = a.ey, ez = a.ez;
-    const int rows = ey * ez;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const size_t plane = (size_t)a.nf1 * a.nf2;
     // Bank-class order (setpts.cu; type-2 plans): the points of a bin are grouped by the shared-memory bank
@@ -925,6 +930,7 @@ interp_tile_kernel(const SIArgs<T> a_in)
     // neighbours collide whenever their cells are a multiple of NC apart (32 % of the wavefronts of the
     // config-5 kernel, profiles/r02f).  Classes are not equally full: slots beyond a class's last point are
     // handed the surplus points of fuller classes, so an item still takes ceil(n / blockDim) rounds.
+    // (A merged tile shifts every cell of a member bin by the same multiple of ex*ey: the classes stay distinct.)
     const int NC = a.bankc;
     const int cls = NC > 0 ? (int)(threadIdx.x % NC) : 0, cap = NC > 0 ? (int)(blockDim.x / NC) : 0;
 
@@ -934,16 +940,31 @@ interp_tile_kernel(const SIArgs<T> a_in)
         __syncthreads();
         const long long w = s_work;
         if (w >= total) break;
-        const int t = (int)(w / nsub), s = (int)(w - (long long)t * nsub);
-        int pstart, n, ox, oy, oz;
-        decode_subproblem<T, DIM>(a, s, pstart, n, ox, oy, oz);
+        int t, ox, oy, oz, ezl = ez;                      // transform, tile origin, z extent of the loaded tile
+        int first_bin = 0, nmember = 1, s_single = 0;
+        if (!merged) {
+            t = (int)(w / nsub);
+            s_single = (int)(w - (long long)t * nsub);
+            int pstart_, n_;
+            decode_subproblem<T, DIM>(a, s_single, pstart_, n_, ox, oy, oz);
+        } else {
+            t = (int)(w / a.npairs);
+            const int pp = (int)(w - (long long)t * a.npairs);
+            const int b1 = pp % a.nb1, b23 = pp / a.nb1, b2 = b23 % a.nb2, bzp = b23 / a.nb2;
+            nmember = min(a.zm, a.nb3 - bzp * a.zm);
+            first_bin = b1 + a.nb1 * (b2 + a.nb2 * (bzp * a.zm));
+            ox = b1 * a.rbs1 - a.pad; oy = b2 * a.rbs2 - a.pad; oz = bzp * a.zm * a.rbs3 - a.pad;
+            ezl = nmember * a.rbs3 + 2 * a.pad;
+            int npts = 0;                                 // nothing to do for a group without points
+            for (int m = 0; m < nmember; ++m) {
+                const size_t b = (size_t)first_bin + (size_t)m * a.nb1 * a.nb2;
+                npts += a.keyoff[(b + 1) * a.cpb] - a.keyoff[b * a.cpb];
+            }
+            if (npts == 0) continue;
+        }
         C *cout = a.c + (size_t)t * a.M;
         const C *fwt = a.fw + (size_t)t * a.fwstride;
-        if (NC > 0 && threadIdx.x < NC) {                 // the class segments of this item's bin
-            const int bin = a.s2b[s];
-            s_cs[threadIdx.x] = a.keyoff[(size_t)bin * a.cpb + threadIdx.x];
-            s_ce[threadIdx.x] = a.keyoff[(size_t)bin * a.cpb + threadIdx.x + 1];
-        }
+        const int rows = ey * ezl;
 
         // ---- tile <- fine grid (async); rows are distributed over the warps
         for (int row = warp; row < rows; row += nwarps) {
@@ -960,7 +981,24 @@ interp_tile_kernel(const SIArgs<T> a_in)
                 if (gx >= 0 && gx < a.nf1) cp_async_cell(trow + lx, grow + gx);
             }
         }
-        if (NC > 0) __syncthreads();                      // s_cls is complete
+        bool first = true;                                // the copy is waited for after the first point's weights
+
+        for (int m = 0; m < nmember; ++m) {
+        const int bin_m = merged ? first_bin + m * a.nb1 * a.nb2 : 0;
+        const int s_lo = merged ? a.substart[bin_m] : s_single, s_hi = merged ? a.substart[bin_m + 1] : s_single + 1;
+        for (int s = s_lo; s < s_hi; ++s) {
+        int pstart, n, oxb, oyb, ozb;
+        decode_subproblem<T, DIM>(a, s, pstart, n, oxb, oyb, ozb);
+        const int zadd = merged ? m * a.rbs3 * ex * ey : 0;   // the member bin's own tile starts this far into the loaded one
+        if (NC > 0) {
+            __syncthreads();                              // the previous item is done with the class segments
+            if (threadIdx.x < NC) {                       // the class segments of this item's bin
+                const int bin = a.s2b[s];
+                s_cs[threadIdx.x] = a.keyoff[(size_t)bin * a.cpb + threadIdx.x];
+                s_ce[threadIdx.x] = a.keyoff[(size_t)bin * a.cpb + threadIdx.x + 1];
+            }
+            __syncthreads();                              // s_cls is complete
+        }
 
         // ---- thread-per-point
         // The bin's points fill R = ceil(n_bin / blockDim) rounds of blockDim slots; slot (class, position) of
@@ -995,7 +1033,6 @@ interp_tile_kernel(const SIArgs<T> a_in)
             }
             return -1;
         };
-        bool first = true;
         for (int i = threadIdx.x; (NC > 0 ? rnd < rnd_end : i < n) || first; i += blockDim.x, ++rnd) {
             const int pidx = NC > 0 ? (rnd < rnd_end ? class_point(rnd) : -1) : (i < n ? pstart + i : -1);
             const bool valid = pidx >= 0;
@@ -1006,16 +1043,16 @@ interp_tile_kernel(const SIArgs<T> a_in)
                 idx = rec_index(rec);
                 const int xs = stencil_start(rec.x, NS);
                 kernel_vector<T, NS, true>(kx, (T)xs - rec.x, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
-                off = clampi(xs - ox, 0, ex - NS);
+                off = clampi(xs - oxb, 0, ex - NS);
                 if (DIM > 1) {
                     const int ys = stencil_start(rec.y, NS);
                     kernel_vector<T, NS, true>(ky, (T)ys - rec.y, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
-                    off += clampi(ys - oy, 0, ey - NS) * ex;
+                    off += clampi(ys - oyb, 0, ey - NS) * ex;
                 }
                 if (DIM > 2) {
                     const int zs = stencil_start(rec.z, NS);
                     kernel_vector<T, NS, true>(kz, (T)zs - rec.z, a.es_c, a.es_beta, a.horner, s_hc, a.ncoef);
-                    off += clampi(zs - a.zshift - oz, 0, ez - NS) * ex * ey;
+                    off += clampi(zs - a.zshift - ozb, 0, ez - NS) * ex * ey + zadd;
                 }
             }
             if (first) {                                  // the tile has landed (weights of the first point overlapped the copy)
@@ -1069,6 +1106,9 @@ interp_tile_kernel(const SIArgs<T> a_in)
             }
             cout[idx] = C{ar, ai};
         }
+        }   // subproblems of the member bin
+        }   // member bins
+        if (first) cp_async_wait_all();                   // (cannot happen: a group with points has an item; keeps the copy accounted for)
     }
 }
 

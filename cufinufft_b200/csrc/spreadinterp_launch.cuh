@@ -40,6 +40,7 @@ static SIArgs<T> make_args(Plan<T> &p, int nt)
     a.es_c = p.es_c; a.es_beta = p.es_beta;
     a.zshift = p.slab ? p.zshift : 0;
     a.bankc = p.bank_classes;
+    a.zm = 1; a.nb3 = p.nbin[2]; a.npairs = 0;
     // experiments only (read once per process): CFB_DIRECT_THR="num/den" = run length below which a batch goes point by point
     static const struct Thr { int n = 0, d = 1; Thr() { if (const char *e = getenv("CFB_DIRECT_THR")) { int a_ = 0, b_ = 1;
                           if (sscanf(e, "%d/%d", &a_, &b_) >= 1 && a_ > 0 && b_ > 0) { n = a_; d = b_; } } } } thr;
@@ -114,8 +115,20 @@ static int do_interp_tile(Plan<T> &p, SIArgs<T> &a, bool &done)
     if (!interp_tile_applies(p)) return 0;
     const size_t head = 18 * 16 * sizeof(T);
     const size_t cells = (size_t)a.ex * a.ey * a.ez;
-    const size_t smem = head + cells * sizeof(C);
+    size_t smem = head + cells * sizeof(C);
     const int threads = (DIM == 3 && smem > 96 * 1024) ? 512 : 256;
+    // one block per SM anyway (wide fp64 stencils in 3-D): let the tile serve as many z-adjacent bins as fit
+    // (interp_tile_kernel: merged); CFB_INTERP_ZM=1 keeps one bin per tile (A/B measurements)
+    if (DIM == 3 && threads == 512 && !p.ilist && a.spbt == 1) {
+        static const int zm_env = [] { const char *e = getenv("CFB_INTERP_ZM"); return e ? atoi(e) : 0; }();
+        for (int zm = zm_env > 0 ? zm_env : 4; zm >= 2; --zm) {
+            const size_t sm = head + (size_t)a.ex * a.ey * (a.rbs3 * zm + 2 * a.pad) * sizeof(C);
+            if (zm <= a.nb3 && sm + 2048 <= (size_t)p.max_smem_optin) {
+                a.zm = zm; a.npairs = a.nb1 * a.nb2 * ((a.nb3 + zm - 1) / zm); smem = sm;
+                break;
+            }
+        }
+    }
     CFB_CUDA_OK(cudaFuncSetAttribute(interp_tile_kernel<T, DIM, NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CFB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, interp_tile_kernel<T, DIM, NS, HORNER>, threads, smem));

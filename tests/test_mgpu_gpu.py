@@ -26,7 +26,7 @@ def _ngpu():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
-@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_slab_transform_with_library_side_collectives(world, dtype):
     if _ngpu() < world:
         pytest.skip("needs >= %d GPUs (gpurun --gpus %d)" % (world, world))
