@@ -383,7 +383,7 @@ def time_reference_gpu(cfg, pts_arr, c, fk, ours_out, torch, stream, npdt, npcd,
         # the reference C API's own batch heuristic (maxbatchsize = 0 -> min(ntransf, 8)); its default evaluator
         ref = reflib.RefPlan(cfg["type"], cfg["modes"], cfg["tol"], npdt, ntransf=nt, maxbatch=0 if nt > 1 else 1, **cfg["opts"])
 
-        def timed(fn, n):
+        def timed(fn, n, stat=np.median):
             fn()
             torch.cuda.synchronize()
             ts = []
@@ -394,9 +394,10 @@ def time_reference_gpu(cfg, pts_arr, c, fk, ours_out, torch, stream, npdt, npcd,
                 e1.record(stream)
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
-            return float(np.median(ts))
+            return float(stat(ts))
 
-        t_set = timed(lambda: ref.set_pts(pts_arr), 2)
+        t_set = timed(lambda: ref.set_pts(pts_arr), 5)          # it cudaMallocs inside setpts: noisy, hence five calls
+        t_set_min = timed(lambda: ref.set_pts(pts_arr), 3, np.min)
         c2 = c.clone() if cfg["type"] == 2 else c
         fk2 = fk.clone() if cfg["type"] == 1 else fk
         t_exec = timed(lambda: ref.execute(TArr(c2, npcd), TArr(fk2, npcd)), reps)
@@ -406,7 +407,7 @@ def time_reference_gpu(cfg, pts_arr, c, fk, ours_out, torch, stream, npdt, npcd,
         M = pts_arr[0].size
         return {"available": True, "library": "cuFINUFFT v1.3 built for sm_100 (oracle/_ref/libcufinufft_ref.so), same device buffers",
                 "ref_exec_ms": t_exec, "ours_exec_ms": ours_exec_ms, "speedup_exec": t_exec / ours_exec_ms,
-                "ref_setpts_ms": t_set, "ours_setpts_ms": ours_setpts_ms, "speedup_setpts": t_set / ours_setpts_ms,
+                "ref_setpts_ms": t_set, "ref_setpts_min_ms": min(t_set, t_set_min), "ours_setpts_ms": ours_setpts_ms, "speedup_setpts": t_set / ours_setpts_ms,
                 "ref_pts_per_s": M * nt / (t_exec * 1e-3), "rel_l2_ours_vs_ref": rel,
                 "evaluator": "gpu_kerevalmeth=%d on both sides" % cfg["opts"].get("gpu_kerevalmeth", 0)}
     except Exception as exc:   # noqa: BLE001
@@ -544,7 +545,8 @@ def run_plain(args, cfg_id, cfg, ctx, steps, warmup, with_e2e=True, with_cpu=Tru
         torch.cuda.synchronize()
         ours_out = (fk if cfg["type"] == 1 else c).clone()
         exec_ms = float(np.median([s["total_ms"] for s in stage_ms])) if ntransf <= geo["maxbatch"] else ms_step
-        vs_ref = time_reference_gpu(dict(cfg, nt_local=ntransf), parr, c, fk, ours_out, torch, stream, npdt, npcd, exec_ms, setpts_ms)
+        vs_ref = time_reference_gpu(dict(cfg, nt_local=ntransf), parr, c, fk, ours_out, torch, stream, npdt, npcd, exec_ms, setpts_ms,
+                                    reps=1 if cfg.get("dist") == "onebin" else 3)
         del ours_out
     barrier()
 
@@ -828,9 +830,13 @@ def main():
 
     extra = {}
     if not explicit and not args.no_extra and args.scale == 1.0:
-        def sub(name, cid, fn, **kw):
+        def sub(name, cid, fn, opts=None, **kw):
             try:
-                rec = fn(args, cid, dict(CONFIGS[cid]), ctx, **kw)
+                c_ = dict(CONFIGS[cid])
+                if opts:
+                    c_["opts"] = dict(c_["opts"], **opts)
+                    c_["name"] += " " + " ".join("%s=%s" % kv for kv in opts.items())
+                rec = fn(args, cid, c_, ctx, **kw)
             except Exception as exc:   # noqa: BLE001
                 rec = {"error": repr(exc)}
                 torch.cuda.empty_cache()
@@ -841,7 +847,9 @@ def main():
         if world == 1:
             for cid in (1, 2, 4, 7):
                 sub("cfg%d" % cid if cid != 7 else "cfg4_type2", cid, run_plain, steps=k, warmup=3, with_e2e=False, with_cpu=False)
-            sub("cfg3_onebin", 8, run_plain, steps=k, warmup=3, with_e2e=False, with_cpu=False, with_ref=False)
+            # Horner against Horner (gpu_kerevalmeth=1 on both sides; the headline compares the default evaluators)
+            sub("cfg3_horner", 3, run_plain, opts=dict(gpu_kerevalmeth=1), steps=k, warmup=3, with_e2e=False, with_cpu=False)
+            sub("cfg3_onebin", 8, run_plain, steps=k, warmup=3, with_e2e=False, with_cpu=False)
             if torch.cuda.mem_get_info()[0] > 150 * 2 ** 30:
                 sub("cfg5_slab_1gpu", 5, run_slab, steps=3, warmup=3, with_e2e=False, with_cpu=False)
         else:

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "cfb_plan.h"
+#include "horner_const.cuh"
 
 namespace cfb {
 
@@ -193,19 +194,26 @@ __device__ __forceinline__ void kernel_vector(T *dst, T x1, T es_c, T es_beta, b
             }
         }
     } else {
+        // Horner: coefficients straight from constant memory (horner_const.cuh; every index is a compile-time
+        // constant once unrolled: the coefficient is the constant-bank operand of its FMA).  `hc` / `ncoef` (the
+        // plan's device copy of the same table) are not read any more.
+        constexpr int NC = cfb_hc_ncoef(NS);
+        const T *tab = HornerTable<T>::at(cfb_hc_off(NS));
         const T z = (T)(2 * (double)x1 + NS - 1.0);
         if (UNROLL) {
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
-                T acc = hc[(ncoef - 1) * NS + i];
-                for (int k = ncoef - 2; k >= 0; --k) acc = fma(z, acc, hc[k * NS + i]);
+                T acc = tab[(NC - 1) * NS + i];
+#pragma unroll
+                for (int k = NC - 2; k >= 0; --k) acc = fma(z, acc, tab[k * NS + i]);
                 dst[i] = acc;
             }
         } else {
 #pragma unroll 1
             for (int i = 0; i < NS; ++i) {
-                T acc = hc[(ncoef - 1) * NS + i];
-                for (int k = ncoef - 2; k >= 0; --k) acc = fma(z, acc, hc[k * NS + i]);
+                T acc = tab[(NC - 1) * NS + i];
+#pragma unroll
+                for (int k = NC - 2; k >= 0; --k) acc = fma(z, acc, tab[k * NS + i]);
                 dst[i] = acc;
             }
         }

@@ -289,14 +289,10 @@ template <int N> struct RunAcc<double, N> {
     __device__ __forceinline__ double2 get(int it) const { return make_double2(ax[it], ay[it]); }
 };
 
+// (The Horner coefficients used to be staged in shared memory here; kernel_vector now reads them from constant
+// memory.  The 18*16*sizeof(T) bytes at the head of every kernel's dynamic shared memory are unused.)
 template <typename T, int NS>
-__device__ __forceinline__ const T *stage_horner(const SIArgs<T> &a, T *s_hc)
-{
-    if (a.horner)
-        for (int i = threadIdx.x; i < a.ncoef * NS; i += blockDim.x) s_hc[i] = a.hcoef[i];
-    __syncthreads();
-    return s_hc;
-}
+__device__ __forceinline__ const T *stage_horner(const SIArgs<T> &, T *s_hc) { __syncthreads(); return s_hc; }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
