@@ -66,6 +66,10 @@ CONFIGS = {
     9: dict(name="cfg5-eighth: 3D type 2 fp64 256^3 (512^3 fine grid) M=1.25e8 uniform tol=1e-9 (config 5's density, one GPU, undivided plan)",
             type=2, modes=(256, 256, 256), M=125_000_000, tol=1e-9, dtype="float64", dist="uniform", ntransf=1,
             opts=dict(gpu_method=1, gpu_sort=1)),
+    # ... and of its type-1 twin (config 6): 3-D fp64 spreading with a 10-wide stencil at config 5's density
+    10: dict(name="cfg6-eighth: 3D type 1 fp64 256^3 (512^3 fine grid) M=1.25e8 uniform tol=1e-9 method 2 (config 6's density, one GPU, undivided plan)",
+             type=1, modes=(256, 256, 256), M=125_000_000, tol=1e-9, dtype="float64", dist="uniform", ntransf=1,
+             opts=dict(gpu_method=2)),
 }
 
 METRIC = "NU points/s per execute"

@@ -149,6 +149,7 @@ struct Plan {
     int tile_cells = 0;
     int tile_cost = 0;                   // shared-memory wavefronts per point of the chosen tile layout (bank-conflict model)
     int sm_warps = 0;                    // warps per block for the SM spread kernel (0 = SM unusable)
+    bool plane_engine = false;           // spread_plane.cuh serves this plan's points (chosen in setpts)
     int interp_engine = 0;               // 0 auto (tile when sorted and it fits), 1 gather, 2 tile
     int bank_classes = 0;                // > 0: the points of the last setpts are in bank-class order (setpts.cu)
     // z-slab decomposition of one 3-D transform (slab.cu): this plan owns the fine-grid

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "spreadinterp.cuh"
 #include "spread_sm2.cuh"
+#include "spread_plane.cuh"
 
 #ifndef CFB_TILE_PAD_PCT
 #define CFB_TILE_PAD_PCT 130
@@ -122,6 +123,37 @@ void plan_tile_geometry(Plan<T> &p)
     p.sm_warps = (int)w;
 }
 
+// The plane-owner engine (spread_plane.cuh: double precision, 3-D, ns >= 9, gpu_method 2): the block's tile is the
+// whole reference bin with its halo, the row stride = ns (mod 8) cells (conflict-free 16-byte cells per quarter-warp).
+// Returns false when it does not apply or the tile + batch scratch do not fit; the warp-private engine then serves.
+template <typename T>
+static bool plane_geometry(Plan<T> &p)
+{
+    p.plane_engine = false;
+    if constexpr (sizeof(T) == 8) {
+        static const bool off = [] { const char *e = getenv("CFB_PLANE"); return e && e[0] == '0'; }();   // A/B measurements
+        if (off || !(p.type == 1 && p.method == 2 && p.sorted && p.dim == 3 && plane_engine_ns(p.ns))) return false;
+        const int pad = (p.ns + 1) / 2;
+        const int ex = p.bs[0] + 2 * pad, ey = p.bs[1] + 2 * pad, ez = p.bs[2] + 2 * pad;
+        const size_t slot = (size_t)((((4 * p.ns) / 2) | 1) * 2);
+        auto bytes = [&](long long cells) {
+            return 18 * 16 * sizeof(T) + (size_t)cells * 2 * sizeof(T) + 128 * slot * sizeof(double) + 2 * 128 * sizeof(int) + 1024;
+        };
+        int sy = ex;
+        while (sy % 8 != p.ns % 8) ++sy;
+        if (bytes((long long)sy * ey * ez) > (size_t)p.max_smem_optin) sy = ex;      // no room for the conflict-free stride
+        const long long cells = (long long)sy * ey * ez;
+        if (cells > (1 << 24) || bytes(cells) > (size_t)p.max_smem_optin) return false;
+        for (int d = 0; d < 3; ++d) { p.ibs[d] = p.bs[d]; p.spb[d] = 1; }
+        p.nibins = p.nbins;
+        p.tile_pad = pad; p.tile_sy = sy; p.tile_sz = sy * ey; p.tile_cells = (int)cells; p.tile_cost = 0;
+        p.sm_warps = ez < 16 ? (ez < 4 ? 4 : ez) : 16;     // >= 4 warps: phase A takes 128 threads
+        p.plane_engine = true;
+        return true;
+    }
+    return false;
+}
+
 // Internal bins for the SM spread engine.  The reference's bins (16x16x2 in 3-D, 32x32 in 2-D) give
 // every warp a private tile of 20-40 KB, i.e. 5-12 resident warps per SM, and the kernel is then
 // bound by the dependent-issue rate of those few warps (profiles/r01k: 30 % issue slots used, stall
@@ -136,8 +168,17 @@ void choose_internal_bins(Plan<T> &p, long long M)
     p.nibins = p.nbins;
     p.imaxsub = p.opts.gpu_maxsubprobsize;
     p.ilist = false;
+    p.plane_engine = false;
     plan_tile_geometry(p);
     if (!(p.type == 1 && p.method == 2 && p.sorted) || p.dim == 1) return;
+    if (plane_geometry(p)) {
+        // one tile per block: no sub-bins; larger work items still save flushes on dense inputs
+        const long long per_item = M / (16LL * p.num_sms);
+        const long long lo = p.opts.gpu_maxsubprobsize, hi = 4096;
+        p.imaxsub = (int)(per_item < lo ? lo : (per_item > hi ? (hi > lo ? hi : lo) : per_item));
+        p.ilist = p.imaxsub != p.opts.gpu_maxsubprobsize;
+        return;
+    }
     // Work-item size of the engines' own list: every item ends with a flush of its tile to the fine
     // grid (15 % of the config-3 kernel's instructions with 1024-point items), so dense inputs get
     // items of up to 4096 points -- as long as >= 16 items per resident warp remain for balance.

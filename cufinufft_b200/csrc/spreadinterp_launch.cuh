@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include "spreadinterp.cuh"
 #include "spread_sm2.cuh"
+#include "spread_plane.cuh"
 
 namespace cfb {
 
@@ -69,6 +70,19 @@ static int do_spread_h(Plan<T> &p, SIArgs<T> &a)
             if (blocks_per_sm * warps > 32) blocks_per_sm = 32 / warps > 0 ? 32 / warps : 1;
             CFB_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(int), p.stream));
             spread_sm2_kernel<DIM, NS, HORNER><<<p.num_sms * blocks_per_sm, 32 * warps, smem, p.stream>>>(a);
+            p.launches_exec++;
+            CFB_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+    }
+    if constexpr (sizeof(T) == 8 && DIM == 3 && plane_engine_ns(NS)) {
+        // double precision, 3-D, wide stencils: the block owns the tile, the warps its planes (spread_plane.cuh)
+        if (p.method == 2 && p.plane_engine) {
+            const int warps = std::min(p.sm_warps, GeoP<NS>::MAXW);
+            const size_t smem = head + (size_t)p.tile_cells * sizeof(C) + GeoP<NS>::SCRATCH;
+            CFB_CUDA_OK(cudaFuncSetAttribute(spread_plane_kernel<NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CFB_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(int), p.stream));
+            spread_plane_kernel<NS, HORNER><<<p.num_sms, 32 * warps, smem, p.stream>>>(a);
             p.launches_exec++;
             CFB_CUDA_OK(cudaGetLastError());
             return 0;

@@ -72,7 +72,16 @@ def test_workplan_invariants(cfg):
         assert w["tile_sz"] >= w["tile_sy"] * ey
     assert w["tile_cells"] >= ex * ey * ez
     cell_bytes = 8 if dtype == np.float32 else 16
-    if w["sm_warps"] > 0:
+    ns = int(np.ceil(-np.log10(tol / 10.0)))
+    plane = dtype == np.float64 and dim == 3 and nufft_type == 1 and ns >= 9 and opts.get("gpu_method", 2) == 2
+    if plane and ns > 10:
+        pass        # wider stencils: the engine applies only while its tile fits (ns = 13: 230 KB, the warp-private engine serves)
+    elif plane:
+        # the plane-owner engine (csrc/spread_plane.cuh): ONE tile per block = the whole reference bin, never split,
+        # row stride = ns (mod 8) cells, a warp per tile plane; tile + the 128-point batch scratch fit the SM
+        assert w["nibins"] == w["nbins"] and w["tile_sy"] % 8 == ns % 8 and w["sm_warps"] == min(ez, 16)
+        assert w["tile_cells"] * cell_bytes + 128 * ((((4 * ns) // 2) | 1) * 2) * 8 + 4096 <= 227 * 1024
+    elif w["sm_warps"] > 0:
         assert w["sm_warps"] * w["tile_cells"] * cell_bytes <= 227 * 1024
     if dim == 1:
         assert w["nibins"] == w["nbins"]                                   # 1-D is never split
@@ -104,8 +113,13 @@ def test_sparse_inputs_and_type2_keep_the_reference_bins():
 
 
 def test_wide_fp64_stencils_are_split_until_four_warps_fit():
-    # 3-D fp64 ns = 10: the reference's bin needs a 130 KB tile (one warp per SM); the split goes on
-    # regardless of density while fewer than four warps fit
-    w = workplan(1, (512, 512, 512), 1e-9, np.float64, 1_000_000)
+    # 3-D fp64 ns = 8 (the widest stencil the warp-private engine still serves in double precision): the
+    # reference's bin needs a 92 KB tile (two warps per SM); the split goes on regardless of density while
+    # fewer than four warps fit
+    w = workplan(1, (512, 512, 512), 1e-7, np.float64, 1_000_000)
     assert w["nibins"] > w["nbins"]
     assert w["sm_warps"] >= 3 or min(w["ibsx"], w["ibsy"]) <= 4
+    # ns = 10: the plane-owner engine takes over -- one block-shared 26 x 26 x 12 tile, no split
+    w = workplan(1, (512, 512, 512), 1e-9, np.float64, 1_000_000)
+    assert w["nibins"] == w["nbins"] and (w["ibsx"], w["ibsy"], w["ibsz"]) == (16, 16, 2)
+    assert w["tile_sy"] == 26 and w["tile_sz"] == 26 * 26 and w["sm_warps"] == 12
