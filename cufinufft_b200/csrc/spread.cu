@@ -137,7 +137,7 @@ static bool plane_geometry(Plan<T> &p)
         const int ex = p.bs[0] + 2 * pad, ey = p.bs[1] + 2 * pad, ez = p.bs[2] + 2 * pad;
         const size_t slot = (size_t)((((4 * p.ns) / 2) | 1) * 2);
         auto bytes = [&](long long cells) {
-            return 18 * 16 * sizeof(T) + (size_t)cells * 2 * sizeof(T) + 128 * slot * sizeof(double) + 2 * 128 * sizeof(int) + 1024;
+            return 18 * 16 * sizeof(T) + (size_t)cells * 2 * sizeof(T) + CFB_PLANE_PB * slot * sizeof(double) + 2 * CFB_PLANE_PB * sizeof(int) + 1024;
         };
         int sy = ex;
         while (sy % 8 != p.ns % 8) ++sy;
@@ -147,7 +147,7 @@ static bool plane_geometry(Plan<T> &p)
         for (int d = 0; d < 3; ++d) { p.ibs[d] = p.bs[d]; p.spb[d] = 1; }
         p.nibins = p.nbins;
         p.tile_pad = pad; p.tile_sy = sy; p.tile_sz = sy * ey; p.tile_cells = (int)cells; p.tile_cost = 0;
-        p.sm_warps = ez < 16 ? (ez < 4 ? 4 : ez) : 16;     // >= 4 warps: phase A takes 128 threads
+        p.sm_warps = ez < 16 ? (ez < CFB_PLANE_PB / 32 ? CFB_PLANE_PB / 32 : ez) : 16;     // phase A takes CFB_PLANE_PB threads
         p.plane_engine = true;
         return true;
     }

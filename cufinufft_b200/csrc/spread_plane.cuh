@@ -12,11 +12,15 @@
 // one 8-byte load of kx[ix], one of ky per row, one 16-byte load of (kz c_re, kz c_im) for the plane, and per row
 // LDS.128 / 2 DFMA / STS.128 on the tile.  The row stride of the tile is chosen = ns (mod 8) cells, which makes the
 // 16-byte cells of a quarter-warp fall on 8 different bank groups (plan_tile_geometry).
-//   phase A (thread per point, 128 points per batch): record, strength, 3 x ns kernel values -> the batch scratch
+//   phase A (thread per point, 256 points per batch): record, strength, 3 x ns kernel values -> the batch scratch
 //   phase B (warp per plane): as above
 //   flush (whole block): tile -> fine grid with RED over the non-zero cells, tile cleared on the way
 #pragma once
 #include "spreadinterp.cuh"
+
+#ifndef CFB_PLANE_PB
+#define CFB_PLANE_PB 256
+#endif
 
 namespace cfb {
 
@@ -24,7 +28,7 @@ template <int NS> struct GeoP {
     static constexpr int RG = 32 / NS;                       // row groups per pass
     static constexpr int LANES = RG * NS;
     static constexpr int NPASS = (NS + RG - 1) / RG;
-    static constexpr int PB = 128;                           // points per batch
+    static constexpr int PB = CFB_PLANE_PB;                  // points per batch
     static constexpr int SLOT = (((4 * NS) / 2) | 1) * 2;    // doubles per point: kx[NS] | ky[NS] | (kz c_re, kz c_im)[NS], odd in 16-byte units
     static constexpr size_t SCRATCH = (size_t)PB * SLOT * sizeof(double) + 2 * PB * sizeof(int);
     static constexpr int MAXW = 16;                          // warps per block (one per tile plane when ez <= 16)

@@ -185,6 +185,36 @@ def test_coarse_partitioned_sort(case, levels):
     assert plan.launch_counts()["setpts"] == plan0.launch_counts()["setpts"] + 5      # count, 3-phase scan, scatter ran
 
 
+# Double precision, 3-D, stencils of nine points and more with gpu_method 2: the plane-owner spreading engine
+# (csrc/spread_plane.cuh: one block-shared tile per reference bin, a warp per z plane).  The reference refuses these
+# plans (its tile exceeds 48 KB of shared memory), so the truth is the oracle and our own GM engine.
+PLANE_CASES = [
+    ((20, 18, 16), 30_000, 1e-9, "uniform", {}),                                   # ns = 10
+    ((24, 20, 16), 200_000, 1e-9, "cluster", {}),                                  # several batches and work items per bin
+    ((16, 16, 16), 60_000, 1e-8, "onebin", {}),                                    # ns = 9 (the conflict-free stride does not fit: natural stride)
+    ((16, 14, 12), 20_000, 1e-10, "wide", {}),                                     # ns = 11
+    ((20, 18, 16), 30_000, 1e-9, "uniform", dict(gpu_kerevalmeth=1)),              # Horner
+    ((20, 18, 16), 30_000, 1e-9, "uniform", dict(gpu_binsizex=8, gpu_binsizey=12, gpu_binsizez=3)),   # other bins: 13 tile planes
+    ((20, 18, 16), 50_000, 1e-9, "cluster", dict(gpu_maxsubprobsize=300)),
+]
+
+
+@pytest.mark.parametrize("case", PLANE_CASES, ids=lambda c: "%s-M%d-%g-%s%s" % ("x".join(map(str, c[0])), c[1], c[2], c[3], "".join("-%s%s" % kv for kv in c[4].items())))
+def test_plane_owner_spread_engine(case):
+    modes, M, tol, dist, opts = case
+    dtype = np.float64
+    pts = make_points(M, 3, dtype, seed=17, dist=dist)
+    data = make_strengths(M, dtype, ntransf=2)
+    out, plan = gpu_nufft(1, modes, pts, data, tol, dtype, ntransf=2, maxbatch=2, return_plan=True, gpu_method=2, **opts)
+    slack = 40 if dist == "onebin" else 1                   # sqrt(M) * eps accumulation-order noise when every point shares a few cells
+    for t in range(2):
+        ref = orc.nufft(1, modes, pts, data[t], tol, dtype=dtype, kerevalmeth=opts.get("gpu_kerevalmeth", 0))
+        assert rel_l2(out[t], ref) <= TOL_PARITY[dtype] * slack
+    gm = gpu_nufft(1, modes, pts, data, tol, dtype, ntransf=2, maxbatch=2, **dict(opts, gpu_method=1))
+    assert rel_l2(out, gm) <= TOL_PARITY[dtype] * slack
+    _check_bins(plan, pts, dtype, opts.get("gpu_maxsubprobsize", 1024))
+
+
 # Nonstandard upsampling factors (opts.upsampfac != 2: kernel width and beta from the cutoff formulas of
 # contrib/spreadinterp.cpp:43-62, fine grid sigma * modes; direct kernel evaluation only).  The reference
 # accepts them through the same opts field; sigma = 1.25 shrinks the fine grid of a 3-D transform 4x.

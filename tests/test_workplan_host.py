@@ -78,9 +78,9 @@ def test_workplan_invariants(cfg):
         pass        # wider stencils: the engine applies only while its tile fits (ns = 13: 230 KB, the warp-private engine serves)
     elif plane:
         # the plane-owner engine (csrc/spread_plane.cuh): ONE tile per block = the whole reference bin, never split,
-        # row stride = ns (mod 8) cells, a warp per tile plane; tile + the 128-point batch scratch fit the SM
+        # row stride = ns (mod 8) cells, a warp per tile plane; tile + the 256-point batch scratch fit the SM
         assert w["nibins"] == w["nbins"] and w["tile_sy"] % 8 == ns % 8 and w["sm_warps"] == min(ez, 16)
-        assert w["tile_cells"] * cell_bytes + 128 * ((((4 * ns) // 2) | 1) * 2) * 8 + 4096 <= 227 * 1024
+        assert w["tile_cells"] * cell_bytes + 256 * ((((4 * ns) // 2) | 1) * 2) * 8 + 4096 <= 227 * 1024
     elif w["sm_warps"] > 0:
         assert w["sm_warps"] * w["tile_cells"] * cell_bytes <= 227 * 1024
     if dim == 1:
