@@ -860,6 +860,9 @@ def main():
             sub("cfg4_sharded", 4, run_plain, steps=k, warmup=3, with_cpu=False, with_ref=False)
             sub("cfg5_type1_slab", 6, run_slab, steps=3, warmup=3, with_e2e=False, with_cpu=False)
     if rank == 0:
+        if world > 1:
+            line["scaling_note"] = ("strong scaling of config 5; the same workload on ONE GPU is the record extra.cfg5_slab_1gpu "
+                                    "of the `--gpus 1` line (whose headline is config 3, the north-star single-GPU target)")
         if extra:
             line["extra"] = extra
         line["wall_s"] = time.perf_counter() - t_wall
