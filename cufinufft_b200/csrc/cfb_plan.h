@@ -148,6 +148,7 @@ struct Plan {
     int tile_sy = 0, tile_sz = 0;        // padded strides (cells)
     int tile_cells = 0;
     int tile_cost = 0;                   // shared-memory wavefronts per point of the chosen tile layout (bank-conflict model)
+    int sm2_rmc = 0;                     // spread_sm2_kernel<3, 6>: row-order class chosen with the tile strides (spread_sm2.cuh: sm2_rowmap_tab)
     int sm_warps = 0;                    // warps per block for the SM spread kernel (0 = SM unusable)
     bool plane_engine = false;           // spread_plane.cuh serves this plan's points (chosen in setpts)
     int interp_engine = 0;               // 0 auto (tile when sorted and it fits), 1 gather, 2 tile

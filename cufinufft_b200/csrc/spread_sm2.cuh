@@ -51,6 +51,27 @@ template <int DIM, int NS> struct Geo2 {
     static constexpr int MAXW = NPASS > 8 ? 8 : 16;                    // warps per block (register budget)
 };
 
+// Row orders of the 3-D ns = 6 kernel (config 3): stencil row (iz*6 + iy) of (pass, row slot), -1 = none.  Class 0 is
+// the natural order.  For the tile strides (sy, sz) = (14, 5) mod 16 [class 1: the 14 x 14 x 8 tile of 8 x 8 x 2 sub-bins
+// with one cell of padding per plane] and (6, 3) mod 16 [class 2: the 22 x 22 x 8 tile of the reference's own bins] the
+// orders below make the 16 lanes of every half-warp of a run flush touch 16 different 8-byte bank pairs
+// (tools/search_sm2_rowmap.py; all classes it found: sm2_rowmaps.inc).  The table is a compile-time constant so that
+// phase A still writes the row weights of a row slot's passes next to each other (one LDS.128 in phase B).
+constexpr int SM2_RMC_COUNT = 3;
+// stencil row served by row slot rr in pass it (-1: none); RMC > 0 only for DIM == 3, NS == 6
+template <int DIM, int NS, int RMC>
+__host__ __device__ constexpr int sm2_row(int it, int rr)
+{
+    constexpr int XP = (NS + 1) / 2, R = 32 / XP, ROWS = DIM == 2 ? NS : NS * NS;
+    constexpr signed char tab[SM2_RMC_COUNT][40] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, -1, -1, -1, -1},
+    {0, 2, 5, 7, 21, 9, 3, 6, 10, 16, 1, 4, 8, 11, 15, 22, 12, 17, 19, 23, 13, 18, 20, 25, 32, 27, 24, 29, 31, 34, 14, 26, 28, 30, 33, 35, -1, -1, -1, -1},
+    {0, 1, 2, 6, 7, 8, 3, 4, 9, 10, 5, 11, 15, 17, 21, 23, 13, 14, 19, 20, 12, 18, 24, 25, 30, 31, 16, 22, 26, 32, 27, 28, 29, 33, 34, 35, -1, -1, -1, -1},
+};
+    if (RMC > 0) return tab[RMC][it * R + rr];
+    return it * R + rr < ROWS ? it * R + rr : -1;
+}
+
 constexpr bool sm2_applies(int dim, int ns) { return dim == 2 || (dim == 3 && ns <= 7); }
 
 // host mirror of the lane mapping, for the tile-layout search (spread.cu: layout_cost)
@@ -70,7 +91,7 @@ inline Sm2Map sm2_map(int dim, int ns)
 // values for the register allocator, and a (w, w) operand becomes the scalar-broadcast form of FFMA2
 __device__ __forceinline__ void fma2(float2 &d, float2 a, float2 b) { d = __ffma2_rn(a, b, d); }
 
-template <int DIM, int NS, bool HORNER>
+template <int DIM, int NS, bool HORNER, int RMC = 0>
 __global__ void __launch_bounds__(32 * Geo2<DIM, NS>::MAXW)
 spread_sm2_kernel(const SIArgs<float> a_in)
 {
@@ -91,13 +112,23 @@ spread_sm2_kernel(const SIArgs<float> a_in)
     constexpr int NCOL = G::SINGLE ? NS : G::XP;                       // lanes per row
     const bool active = lane < G::LANES;
     const int r = active ? lane / NCOL : 0, ix = active ? lane - r * NCOL : 0;
-    const bool last_ok = active && (G::NPASS - 1) * G::R + r < G::ROWS;     // the last pass may run past the stencil
+    // stencil row of this lane's row slot per pass (SINGLE: row = r)
+    auto row_of = [&](int it) -> int {
+        if constexpr (G::SINGLE) return r < G::ROWS ? r : -1;
+        else {
+            int row = -1;
+#pragma unroll
+            for (int rr = 0; rr < G::R; ++rr) if (rr == r) row = sm2_row<DIM, NS, RMC>(it, rr);
+            return row;
+        }
+    };
+    const bool last_ok = active && row_of(G::NPASS - 1) >= 0;          // the last pass may run past the stencil
     const bool b_ok = G::SINGLE || ix + G::XP < NS;                    // odd widths: the last pair has one column only
     int tb[G::NPASS];                                                  // tile offset of this lane's (first) cell per pass
 #pragma unroll
     for (int it = 0; it < G::NPASS; ++it) {
-        int row = it * G::R + r;
-        if (row >= G::ROWS) row = 0;
+        int row = row_of(it);
+        if (row < 0) row = 0;
         if (DIM == 2) tb[it] = row * a.sy + ix;
         else { const int iz = row / NS, iy = row - iz * NS; tb[it] = iz * a.sz + iy * a.sy + ix; }
     }
@@ -207,7 +238,9 @@ spread_sm2_kernel(const SIArgs<float> a_in)
                     // row slot rr, pass it -> flat float index rr*WS + it inside the W segment
                     auto wv = [&](int f) -> float {
                         const int rr = f / G::WS, it = f - rr * G::WS;
-                        return (rr < G::R && it < G::NPASS) ? wrow(it * G::R + rr) : 0.0f;
+                        if (!(rr < G::R && it < G::NPASS)) return 0.0f;
+                        const int row = sm2_row<DIM, NS, RMC>(it, rr);     // compile-time after unrolling
+                        return row >= 0 ? wrow(row) : 0.0f;
                     };
 #pragma unroll
                     for (int i = 0; i < G::WSEG / 4; ++i)

@@ -64,12 +64,22 @@ static int do_spread_h(Plan<T> &p, SIArgs<T> &a)
             int warps = std::min(p.sm_warps, Geo2<DIM, NS>::MAXW);
             while (warps > 1 && head + (size_t)warps * per_warp + 1024 > (size_t)p.max_smem_optin) --warps;
             const size_t smem = head + (size_t)warps * per_warp;
-            CFB_CUDA_OK(cudaFuncSetAttribute(spread_sm2_kernel<DIM, NS, HORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int blocks_per_sm = (int)((size_t)p.max_smem_optin / (smem + 1024));
             if (blocks_per_sm < 1) blocks_per_sm = 1;
             if (blocks_per_sm * warps > 32) blocks_per_sm = 32 / warps > 0 ? 32 / warps : 1;
             CFB_CUDA_OK(cudaMemsetAsync(a.counter, 0, sizeof(int), p.stream));
-            spread_sm2_kernel<DIM, NS, HORNER><<<p.num_sms * blocks_per_sm, 32 * warps, smem, p.stream>>>(a);
+            auto go = [&](auto kern) -> int {
+                CFB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<p.num_sms * blocks_per_sm, 32 * warps, smem, p.stream>>>(a);
+                return 0;
+            };
+            int e = 0;
+            if constexpr (DIM == 3 && NS == 6) {            // row-order class picked with the tile strides (spread.cu: plan_tile_geometry)
+                if (p.sm2_rmc == 1) e = go(spread_sm2_kernel<DIM, NS, HORNER, 1>);
+                else if (p.sm2_rmc == 2) e = go(spread_sm2_kernel<DIM, NS, HORNER, 2>);
+                else e = go(spread_sm2_kernel<DIM, NS, HORNER, 0>);
+            } else e = go(spread_sm2_kernel<DIM, NS, HORNER, 0>);
+            if (e) return e;
             p.launches_exec++;
             CFB_CUDA_OK(cudaGetLastError());
             return 0;
