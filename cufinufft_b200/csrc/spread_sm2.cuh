@@ -133,8 +133,10 @@ spread_sm2_kernel(const SIArgs<float> a_in)
         else { const int iz = row / NS, iy = row - iz * NS; tb[it] = iz * a.sz + iy * a.sy + ix; }
     }
     // this lane's operands inside a point slot
-    const float *my_ck = slots + ix * (G::SINGLE ? 2 : 4);
-    const float *my_w = slots + G::CKSEG + r * G::WS;
+    // (the idle lanes 30, 31 of a 10 x 3 mapping read what their neighbour reads: with r = 0 they hit the bank group of
+    // row slot 8 at another address, a fifth wavefront for every weight load -- profiles/r03n)
+    const float *my_ck = slots + (active ? ix : NCOL - 1) * (G::SINGLE ? 2 : 4);
+    const float *my_w = slots + G::CKSEG + (active ? r : G::R - 1) * G::WS;
 
     const int nsub = *a.nsub;
     const long long total = (long long)nsub * a.nt;
