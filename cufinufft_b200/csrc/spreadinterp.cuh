@@ -906,7 +906,7 @@ interp_tile_kernel(const SIArgs<T> a_in)
     T *s_hc = reinterpret_cast<T *>(smem);
     C *tile = reinterpret_cast<C *>(smem + 18 * 16 * sizeof(T));
     __shared__ long long s_work;
-    __shared__ int s_cs[16], s_ce[16];                    // bank-class order: this item's range of every class
+    __shared__ int s_cs[4][16], s_ce[4][16];              // bank-class order: the range of every class in every member bin of the item
     stage_horner<T, NS>(a, s_hc);
 
     const int nsub = *a.nsub;
@@ -978,6 +978,18 @@ interp_tile_kernel(const SIArgs<T> a_in)
             }
         }
         bool first = true;                                // the copy is waited for after the first point's weights
+        if (NC > 0) {
+            // the class segments of every member bin at once: after this barrier the block walks the bins and their
+            // rounds without another one (the tile and these tables are read-only), so the warps drift freely and
+            // the shared-memory pipe does not drain at every bin boundary
+            for (int i = threadIdx.x; i < nmember * NC; i += blockDim.x) {
+                const int m = i / NC, c = i - m * NC;
+                const size_t bin = merged ? (size_t)first_bin + (size_t)m * a.nb1 * a.nb2 : (size_t)a.s2b[s_single];
+                s_cs[m][c] = a.keyoff[bin * a.cpb + c];
+                s_ce[m][c] = a.keyoff[bin * a.cpb + c + 1];
+            }
+            __syncthreads();
+        }
 
         for (int m = 0; m < nmember; ++m) {
         const int bin_m = merged ? first_bin + m * a.nb1 * a.nb2 : 0;
@@ -986,15 +998,7 @@ interp_tile_kernel(const SIArgs<T> a_in)
         int pstart, n, oxb, oyb, ozb;
         decode_subproblem<T, DIM>(a, s, pstart, n, oxb, oyb, ozb);
         const int zadd = merged ? m * a.rbs3 * ex * ey : 0;   // the member bin's own tile starts this far into the loaded one
-        if (NC > 0) {
-            __syncthreads();                              // the previous item is done with the class segments
-            if (threadIdx.x < NC) {                       // the class segments of this item's bin
-                const int bin = a.s2b[s];
-                s_cs[threadIdx.x] = a.keyoff[(size_t)bin * a.cpb + threadIdx.x];
-                s_ce[threadIdx.x] = a.keyoff[(size_t)bin * a.cpb + threadIdx.x + 1];
-            }
-            __syncthreads();                              // s_cls is complete
-        }
+        const int *cs = s_cs[m], *ce = s_ce[m];
 
         // ---- thread-per-point
         // The bin's points fill R = ceil(n_bin / blockDim) rounds of blockDim slots; slot (class, position) of
@@ -1004,7 +1008,7 @@ interp_tile_kernel(const SIArgs<T> a_in)
         int rnd = 0, rnd_end = 0, ccap = 0;
         if (NC > 0) {
             int nbin = 0;
-            for (int c = 0; c < NC; ++c) nbin += s_ce[c] - s_cs[c];
+            for (int c = 0; c < NC; ++c) nbin += ce[c] - cs[c];
             const int bin = a.s2b[s];
             const int k = s - a.substart[bin], K = a.substart[bin + 1] - a.substart[bin];
             const int R = (nbin + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -1014,16 +1018,16 @@ interp_tile_kernel(const SIArgs<T> a_in)
         // sorted point index (absolute) of this thread in round `rnd`, or -1
         auto class_point = [&](int rnd) -> int {
             const int j = rnd * cap + (int)(threadIdx.x / NC);
-            const int mine = s_ce[cls] - s_cs[cls];
-            if (j < mine) return s_cs[cls] + j;
+            const int mine = ce[cls] - cs[cls];
+            if (j < mine) return cs[cls] + j;
             // a free slot: its rank among the free slots (ordered by class, then position) ...
             int k = j - mine;
-            for (int c = 0; c < cls; ++c) k += max(0, ccap - (s_ce[c] - s_cs[c]));
+            for (int c = 0; c < cls; ++c) k += max(0, ccap - (ce[c] - cs[c]));
             // ... takes the surplus point (position >= ccap in a fuller class) of the same rank
             for (int c = 0; c < NC; ++c) {
-                const int over = (s_ce[c] - s_cs[c]) - ccap;
+                const int over = (ce[c] - cs[c]) - ccap;
                 if (over > 0) {
-                    if (k < over) return s_cs[c] + ccap + k;
+                    if (k < over) return cs[c] + ccap + k;
                     k -= over;
                 }
             }

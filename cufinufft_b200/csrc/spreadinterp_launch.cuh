@@ -145,7 +145,7 @@ static int do_interp_tile(Plan<T> &p, SIArgs<T> &a, bool &done)
     // (interp_tile_kernel: merged); CFB_INTERP_ZM=1 keeps one bin per tile (A/B measurements)
     if (DIM == 3 && threads == 512 && !p.ilist && a.spbt == 1) {
         static const int zm_env = [] { const char *e = getenv("CFB_INTERP_ZM"); return e ? atoi(e) : 0; }();
-        for (int zm = zm_env > 0 ? zm_env : 4; zm >= 2; --zm) {
+        for (int zm = zm_env > 0 && zm_env < 4 ? zm_env : 4; zm >= 2; --zm) {     // <= 4: interp_tile_kernel's class tables
             const size_t sm = head + (size_t)a.ex * a.ey * (a.rbs3 * zm + 2 * a.pad) * sizeof(C);
             if (zm <= a.nb3 && sm + 2048 <= (size_t)p.max_smem_optin) {
                 a.zm = zm; a.npairs = a.nb1 * a.nb2 * ((a.nb3 + zm - 1) / zm); smem = sm;
