@@ -7,6 +7,7 @@
 // observe are listed in include/cufinufft.h.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "cfb_plan.h"
@@ -341,10 +342,11 @@ static int setpts_host(Plan<T> *p, int M, const T *x, const T *y, const T *z)
 
     // Type 1 pays for chunks: the spread kernels accumulate runs of points that share a stencil, and dealing the
     // points of a cell to K chunks divides the run length by K.  2-D: 4 chunks still win (config 1: 2.11 -> 1.85 ms
-    // per host-buffer step); 3-D, where a run saves ns^3 tile updates, they lose (config 3, clustered: 26.8 -> 31.4 ms
-    // with 4 chunks; profiles/r02x) -- no chunks there.  Type 2 has no such coupling (config 2: 16.9 -> 14.2 ms).
+    // per host-buffer step); 3-D, where a run saves ns^3 tile updates: two chunks (config 3, clustered: 25.9 -> 24.0 ms;
+    // three give 29.1, four 31.4; profiles/r02x, r03q).  Type 2 has no such coupling (config 2: 16.9 -> 14.2 ms).
+    static const int pipe3d = [] { const char *e = getenv("CFB_PIPE3D"); return e && atoi(e) > 0 ? atoi(e) : 2; }();   // experiments
     const int K = (M >= PIPE_MIN_POINTS && p->ntransf == 1 && !p->slab && !p->opts.gpu_spreadinterponly)
-                      ? (p->type == 1 ? (p->dim <= 2 ? 4 : 1) : 8) : 1;
+                      ? (p->type == 1 ? (p->dim <= 2 ? 4 : pipe3d) : 8) : 1;
     if (K == 1) {
         for (Plan<T> *c : p->chunks) free_plan(c);
         p->chunks.clear();
