@@ -991,14 +991,47 @@ interp_tile_kernel(const SIArgs<T> a_in)
             __syncthreads();
         }
 
-        for (int m = 0; m < nmember; ++m) {
+        // Merged tile with bank classes: the member bins' points are dealt to the rounds JOINTLY (class c's pool is the
+        // concatenation of its segments in the member bins).  A class that is fuller than its share of slots spills
+        // into other classes' free slots, and every such point poisons its quarter-warp with a 2-way conflict for all
+        // 1000 stencil loads: 2 % of the points of ONE 477-point bin are misplaced (class sizes 60 +- 7 against 64
+        // slots), 0.3 % of a four-bin pool (239 +- 14 against 256) -- profiles/r03t: 4.49 -> wavefronts per LDS.128.
+        const bool joint = merged && NC > 0;
+        for (int m = 0; m < (joint ? 1 : nmember); ++m) {
         const int bin_m = merged ? first_bin + m * a.nb1 * a.nb2 : 0;
-        const int s_lo = merged ? a.substart[bin_m] : s_single, s_hi = merged ? a.substart[bin_m + 1] : s_single + 1;
+        const int s_lo = merged ? a.substart[bin_m] : s_single;
+        const int s_hi = joint ? s_lo + 1 : (merged ? a.substart[bin_m + 1] : s_single + 1);
         for (int s = s_lo; s < s_hi; ++s) {
-        int pstart, n, oxb, oyb, ozb;
-        decode_subproblem<T, DIM>(a, s, pstart, n, oxb, oyb, ozb);
-        const int zadd = merged ? m * a.rbs3 * ex * ey : 0;   // the member bin's own tile starts this far into the loaded one
+        int pstart = 0, n = 0, oxb = ox, oyb = oy, ozb = oz;
+        if (!joint) decode_subproblem<T, DIM>(a, s, pstart, n, oxb, oyb, ozb);
+        int zadd = merged ? m * a.rbs3 * ex * ey : 0;         // the member bin's own tile starts this far into the loaded one
         const int *cs = s_cs[m], *ce = s_ce[m];
+        // size of class c: in this bin, or (joint) in the whole group
+        auto csize = [&](int c) -> int {
+            if constexpr (DIM == 3) {
+                if (joint) {
+                    int t_ = 0;
+                    for (int mm = 0; mm < nmember; ++mm) t_ += s_ce[mm][c] - s_cs[mm][c];
+                    return t_;
+                }
+            }
+            return ce[c] - cs[c];
+        };
+        // sorted point index of position j of class c (joint: walks the member bins; also says which member)
+        auto cpoint = [&](int c, int j, int &mm) -> int {
+            mm = m;
+            if constexpr (DIM == 3) {
+                if (joint) {
+                    for (mm = 0; mm < nmember - 1; ++mm) {
+                        const int k_ = s_ce[mm][c] - s_cs[mm][c];
+                        if (j < k_) break;
+                        j -= k_;
+                    }
+                    return s_cs[mm][c] + j;
+                }
+            }
+            return cs[c] + j;
+        };
 
         // ---- thread-per-point
         // The bin's points fill R = ceil(n_bin / blockDim) rounds of blockDim slots; slot (class, position) of
@@ -1008,34 +1041,40 @@ interp_tile_kernel(const SIArgs<T> a_in)
         int rnd = 0, rnd_end = 0, ccap = 0;
         if (NC > 0) {
             int nbin = 0;
-            for (int c = 0; c < NC; ++c) nbin += ce[c] - cs[c];
-            const int bin = a.s2b[s];
-            const int k = s - a.substart[bin], K = a.substart[bin + 1] - a.substart[bin];
+            for (int c = 0; c < NC; ++c) nbin += csize(c);
             const int R = (nbin + (int)blockDim.x - 1) / (int)blockDim.x;
-            rnd = (int)((long long)R * k / K); rnd_end = (int)((long long)R * (k + 1) / K);
+            if (joint) { rnd = 0; rnd_end = R; }
+            else {
+                const int bin = a.s2b[s];
+                const int k = s - a.substart[bin], K = a.substart[bin + 1] - a.substart[bin];
+                rnd = (int)((long long)R * k / K); rnd_end = (int)((long long)R * (k + 1) / K);
+            }
             ccap = R * cap;
         }
-        // sorted point index (absolute) of this thread in round `rnd`, or -1
-        auto class_point = [&](int rnd) -> int {
+        // sorted point index (absolute) of this thread in round `rnd`, or -1; mm = the member bin it belongs to
+        auto class_point = [&](int rnd, int &mm) -> int {
             const int j = rnd * cap + (int)(threadIdx.x / NC);
-            const int mine = ce[cls] - cs[cls];
-            if (j < mine) return cs[cls] + j;
+            const int mine = csize(cls);
+            if (j < mine) return cpoint(cls, j, mm);
             // a free slot: its rank among the free slots (ordered by class, then position) ...
             int k = j - mine;
-            for (int c = 0; c < cls; ++c) k += max(0, ccap - (ce[c] - cs[c]));
+            for (int c = 0; c < cls; ++c) k += max(0, ccap - csize(c));
             // ... takes the surplus point (position >= ccap in a fuller class) of the same rank
             for (int c = 0; c < NC; ++c) {
-                const int over = (ce[c] - cs[c]) - ccap;
+                const int over = csize(c) - ccap;
                 if (over > 0) {
-                    if (k < over) return cs[c] + ccap + k;
+                    if (k < over) return cpoint(c, ccap + k, mm);
                     k -= over;
                 }
             }
+            mm = m;
             return -1;
         };
         for (int i = threadIdx.x; (NC > 0 ? rnd < rnd_end : i < n) || first; i += blockDim.x, ++rnd) {
-            const int pidx = NC > 0 ? (rnd < rnd_end ? class_point(rnd) : -1) : (i < n ? pstart + i : -1);
+            int mm = m;
+            const int pidx = NC > 0 ? (rnd < rnd_end ? class_point(rnd, mm) : -1) : (i < n ? pstart + i : -1);
             const bool valid = pidx >= 0;
+            if (joint) { ozb = oz + mm * a.rbs3; zadd = mm * a.rbs3 * ex * ey; }
             T kx[NS], ky[DIM > 1 ? NS : 1], kz[DIM > 2 ? NS : 1];
             int off = 0, idx = 0;
             if (valid) {
