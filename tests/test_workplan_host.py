@@ -123,3 +123,46 @@ def test_wide_fp64_stencils_are_split_until_four_warps_fit():
     w = workplan(1, (512, 512, 512), 1e-9, np.float64, 1_000_000)
     assert w["nibins"] == w["nbins"] and (w["ibsx"], w["ibsy"], w["ibsz"]) == (16, 16, 2)
     assert w["tile_sy"] == 26 and w["tile_sz"] == 26 * 26 and w["sm_warps"] == 12
+
+
+def test_sm2_row_orders_are_permutations_and_conflict_free():
+    """csrc/spread_sm2.cuh: sm2_row -- the compile-time row orders of the 3-D ns = 6 SM spread kernel.  Every order
+    deals each of the 36 stencil rows to exactly one (pass, row slot); for the stride classes they were searched for
+    (tools/search_sm2_rowmap.py) the 16 lanes of every half-warp of a run flush -- lane = (row slot, column pair), 8-byte
+    cells, 16 bank pairs -- touch 16 different bank pairs, for both columns of the pair.  The strides are the ones the
+    work plan picks for config 3's sub-bins (14, 197) and for the reference's own bins (22, 499)."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cufinufft_b200", "csrc", "spread_sm2.cuh")).read()
+    body = src[src.index("constexpr signed char tab[SM2_RMC_COUNT][40] = {"):]
+    body = body[:body.index("};")]
+    tabs = [[int(v) for v in row.split(",")] for row in re.findall(r"\{([-\d,\s]+)\}", body)]
+    assert len(tabs) == 3 and all(len(t) == 40 for t in tabs)
+    for t in tabs:
+        assert sorted(v for v in t if v >= 0) == list(range(36)) and t[36:] == [-1] * 4
+    assert tabs[0][:36] == list(range(36))
+
+    def conflicts(tab, sy, sz):
+        worst = 0
+        for it in range(4):
+            for half in range(2):                                   # column xp, then column xp + 3
+                for g0 in (0, 16):
+                    seen = {}
+                    for lane in range(g0, min(g0 + 16, 30)):
+                        r, xp = divmod(lane, 3)
+                        row = tab[it * 10 + r]
+                        if row < 0:
+                            continue
+                        iz, iy = divmod(row, 6)
+                        bank = (iz * sz + iy * sy + xp + 3 * half) % 16
+                        seen[bank] = seen.get(bank, 0) + 1
+                    worst = max(worst, max(seen.values(), default=1))
+        return worst
+
+    assert conflicts(tabs[1], 14, 197) == 1 and conflicts(tabs[2], 22, 499) == 1
+    assert conflicts(tabs[0], 14, 196) == 2                       # the natural order on the natural strides: what round 1 measured
+    # and the work plan picks exactly these strides
+    w = workplan(1, (256, 256, 256), 1e-5, np.float32, 100_000_000)
+    assert (w["tile_sy"], w["tile_sz"], w["tile_cost"]) == (14, 197, 16)
+    w = workplan(1, (64, 64, 64), 1e-5, np.float32, 100_000)
+    assert (w["tile_sy"], w["tile_sz"]) == (22, 499)
