@@ -197,6 +197,11 @@ class SlabPlan:
     def set_timing(self, on=True):
         self._fn["set_timing"](self.plan, int(bool(on)))
 
+    def set_sort_levels(self, levels):
+        """A/B and test switch of the point sort (cufinufft*_set_sort_levels; takes effect at the next set_pts)."""
+        if self._fn["set_sort_levels"](self.plan, int(levels)) != 0:
+            raise RuntimeError("Error setting the sort levels.")
+
     def timing(self):
         t = (ctypes.c_float * 5)()
         if self._fn["get_timing"](self.plan, t) != 0:

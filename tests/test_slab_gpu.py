@@ -24,6 +24,10 @@ CASES = [
     ((24, 20, 32), 30000, 1e-5, np.float32, "cluster", dict(gpu_method=1)),      # GM engines
     ((20, 18, 32), 20000, 1e-9, np.float64, "wide", {}),                         # config-5 shape: ns=10 fp64
     ((16, 12, 40), 5000, 1e-3, np.float32, "uniform", dict(gpu_sort=0, gpu_method=1)),
+    # the coarse partition in front of the sort (csrc/setpts.cu; automatic only for key tables beyond L2, e.g. the
+    # type-1 slabs of config 5's size) forced on slab plans: slab-local bins, global z in the records
+    ((24, 20, 32), 30000, 1e-5, np.float32, "cluster", dict(_sort_levels=9)),
+    ((20, 18, 32), 20000, 1e-9, np.float64, "wide", dict(_sort_levels=9)),
 ]
 
 
@@ -45,9 +49,13 @@ def test_emulated_slabs_match_undivided_plan(case, world):
 
     for nufft_type in (1, 2):
         o = dict(opts)
+        sort_levels = o.pop("_sort_levels", 0)
         if nufft_type == 2:
             o.pop("gpu_method", None)
         plans = [SlabPlan(nufft_type, shape, eps=tol, dtype=dtype, rank=r, world=world, **o) for r in range(world)]
+        if sort_levels:
+            for p in plans:
+                p.set_sort_levels(sort_levels)
         g = plans[0].info()
         assert g["nf3"] >= 2 * modes[2] and g["pad"] == (g["ns"] + 1) // 2
         assert [p.info()["z0"] for p in plans] == [r * (g["nf3"] // world) + min(r, g["nf3"] % world) for r in range(world)]
@@ -99,6 +107,10 @@ def test_points_outside_the_slab_are_counted():
     # foreign points whose z rounds onto the slab's upper edge plane are tolerated (stencil inside the halo)
     n_foreign = int(np.sum(owner != 1))
     assert 0.95 * n_foreign <= plan.info()["outside"] <= n_foreign
+    counted = plan.info()["outside"]
+    plan.set_sort_levels(9)                                # the same through the coarse partition: counted once, in its first pass
+    plan.set_pts(*dev)
+    assert plan.info()["outside"] == counted
     c = torch.zeros(4000, dtype=torch.complex64, device="cuda")
     fk = torch.from_numpy(make_modes_data(modes, dtype)[0]).cuda()
     plan.type2(c, fk)                                      # still in bounds: pulled onto the slab edge
